@@ -1,0 +1,88 @@
+"""Autograd bridge: ``render`` as a ``torch.autograd.Function`` backed by the hand-written VJP
+kernel (the analogue of a ``jax.custom_vjp`` around the reference's ``render``)."""
+from __future__ import annotations
+
+import torch
+
+from .. import _native as N
+from .._util import f32, contig
+
+
+def _leaves(tel, sensor_idx):
+    from .render import _get_stages
+    stages = _get_stages(tel.mirror_groups)
+    out = []
+    for g in stages.get(0, []):
+        out += [g.positions, g.rotations, g.perturbation_scale, g.weights]
+    s = tel.sensors[sensor_idx]
+    out += [s.position, s.rotation]
+    return out
+
+
+def needs_grad(tel, sources, values, sensor_idx) -> bool:
+    if not torch.is_grad_enabled():
+        return False
+    ts = _leaves(tel, sensor_idx) + [t for t in (sources, values) if isinstance(t, torch.Tensor)]
+    return any(t.requires_grad for t in ts)
+
+
+class _Render(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tel, source_type, sensor_idx, src, val, *leaves):
+        from . import render as R
+        ctx.tel, ctx.source_type, ctx.sensor_idx = tel, source_type, sensor_idx
+        ctx.save_for_backward(src, val)
+        ctx.n_groups = (len(leaves) - 2) // 4
+        with torch.no_grad():
+            keep = []
+            sc, sensor = R.build_scene(tel, sensor_idx, keep)
+            out = torch.empty(sensor.get_accumulator_shape(), dtype=torch.float32, device=src.device)
+            if sc is None:
+                return out.zero_()
+            N.check(N.lib().iact_render(sc, N.ptr(src), N.ptr(val), src.shape[0], R._stype(source_type), N.ptr(out),
+                                        N.stream_ptr()), "render")
+        return out
+
+    @staticmethod
+    def backward(ctx, g_img):
+        from . import render as R
+        tel, sensor_idx = ctx.tel, ctx.sensor_idx
+        src, val = ctx.saved_tensors
+        stages = R._get_stages(tel.mirror_groups)
+        g_img = contig(g_img.to(torch.float32))
+        dev = src.device
+        g_src = torch.zeros_like(src)
+        g_val = torch.zeros_like(val)
+        g_spos = torch.zeros(3, device=dev)
+        g_srot = torch.zeros(3, device=dev)
+        grads = []
+        keep = []
+        sc, _ = R.build_scene(tel, sensor_idx, keep)
+        off = 0
+        for g in stages.get(0, []):
+            F, M = len(g), g.points.shape[1]
+            gp, gr = torch.zeros((F, 3), device=dev), torch.zeros((F, 3), device=dev)
+            gs, gw = torch.zeros((F,), device=dev), torch.zeros((F, M, 1), device=dev)
+            if sc is not None and F * M:
+                fa = g._facets_struct(keep)
+                sub = N.IactScene.from_buffer_copy(sc)
+                # the VJP kernel walks one group's facets: point the scene at that slice of the tables
+                sub.n_facets = F
+                sub.world = sc.world + off * M * 8 * 4
+                sub.bounds = sc.bounds + off * 4 * 4
+                gr_struct = N.IactGrads(N.ptr(gp), N.ptr(gr), N.ptr(gs), N.ptr(gw), N.ptr(g_val), N.ptr(g_src),
+                                        N.ptr(g_spos), N.ptr(g_srot))
+                N.check(N.lib().iact_render_vjp(sub, fa, N.ptr(src), N.ptr(val), src.shape[0],
+                                                R._stype(ctx.source_type), N.ptr(g_img), gr_struct, N.stream_ptr()),
+                        "render_vjp")
+            grads += [gp, gr, gs, gw]
+            off += F
+        return (None, None, None, g_src, g_val, *grads, g_spos, g_srot)
+
+
+def render_with_grad(tel, sources, values, source_type, sensor_idx):
+    N.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    src = f32(sources, dev).reshape(-1, 3).contiguous()
+    val = f32(values, dev).reshape(-1).contiguous()
+    return _Render.apply(tel, source_type, sensor_idx, src, val, *_leaves(tel, sensor_idx))

@@ -1,0 +1,504 @@
+// K2/K3/K5: forward trace + sensor binning -- render, render_response_matrix, render_debug
+// (reference core/render.py:174-324, _trace_single_mirror :118-157).
+//
+// Work decomposition:
+//   block item  = (source s, chunk of facets)      -> grid-stride over items
+//   warp item   = (facet f, sample range)          -> warps of the block stride over the chunk
+//   lane        = one ray (sample m of facet f seen from source s)
+// A warp first culls the obstruction tables against the (facet, source) beam into a per-warp
+// shared-memory candidate list (warp-uniform, conservative), then its lanes trace rays against
+// that short list.  Hex cameras are binned into a block-private shared-memory histogram that is
+// flushed once per source (response matrix: plain coalesced stores) or once per block (render:
+// one red.global per touched pixel); square cameras use red.global directly.
+#include "iact_trace.cuh"
+#include <algorithm>
+#include <cstring>
+
+namespace {
+
+enum { MODE_RENDER = 0, MODE_MATRIX = 1, MODE_DEBUG = 2 };
+enum { SENS_SQUARE = 0, SENS_HEX = 1 };
+
+struct LaunchPlan {
+    int S, n_chunks, chunk_facets, msplit, msize;
+    long long n_items;
+};
+
+struct Beam { V3 c, u; float R, invD; bool ok; };
+
+// Beam of all rays from the facet's bounding sphere towards the source (and beyond: the reference's
+// shadow ray is infinite, render.py:138 + :40).
+template <int SRC>
+__device__ __forceinline__ Beam make_beam(float4 bnd, V3 src) {
+    Beam b;
+    b.c = v3(bnd.x, bnd.y, bnd.z); b.R = bnd.w;
+    V3 a = SRC == IACT_SOURCE_POINT ? src - b.c : -src;
+    const float n2 = dot(a, a);
+    b.ok = n2 > 1e-30f && n2 < 1e37f;
+    const float inv = rsqrtf(b.ok ? n2 : 1.f);
+    b.u = inv * a;
+    b.invD = SRC == IACT_SOURCE_POINT ? inv : 0.f;
+    if (b.R * b.invD > 0.1f) b.ok = false;              // source inside/near the facet: no culling
+    return b;
+}
+
+// Conservative: false only if no ray of the beam can come within r of the segment [p1,p2].
+__device__ __forceinline__ bool beam_keeps_capsule(const Beam& b, V3 p1, V3 p2, float r) {
+    const V3 a1 = p1 - b.c, a2 = p2 - b.c;
+    const float t1 = dot(a1, b.u), t2 = dot(a2, b.u);
+    const float tmx = fmaxf(t1, t2);
+    const float marg = 2e-3f;
+    if (tmx + r < -(b.R + marg)) return false;          // wholly behind every ray origin
+    const float tmax = 1.02f * (fmaxf(tmx, 0.f) + r + b.R);
+    const float Reff = b.R * (1.0f + 1.5708f * tmax * b.invD) + marg + 1e-5f * tmax;
+    const V3 q1 = a1 - t1 * b.u, q2 = a2 - t2 * b.u;
+    const V3 e = q2 - q1;
+    const float ee = dot(e, e);
+    const float s = ee > 1e-20f ? fminf(fmaxf(-dot(q1, e) / ee, 0.f), 1.f) : 0.f;
+    const V3 dv = q1 + s * e;
+    const float lim = Reff + r;
+    return dot(dv, dv) <= lim * lim;
+}
+__device__ __forceinline__ bool beam_keeps_ball(const Beam& b, V3 m, float rho) {
+    return beam_keeps_capsule(b, m, m, rho);
+}
+
+// Warp-cooperative compaction of the candidate primitives; returns total, sets n_cyl.
+__device__ __forceinline__ int build_list(const ObsSmem& ob, const Beam& b, unsigned short* list, int& n_cyl_out) {
+    const unsigned lane = threadIdx.x & 31u;
+    int n = 0;
+    for (int base = 0; base < ob.n_cyl; base += 32) {
+        const int i = base + (int)lane;
+        bool keep = false;
+        if (i < ob.n_cyl) {
+            const float* c = ob.cyl + CYL_STRIDE * i;
+            const V3 p1 = v3(c[0], c[1], c[2]);
+            keep = !b.ok || beam_keeps_capsule(b, p1, p1 + c[6] * v3(c[3], c[4], c[5]), c[7]);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) list[n + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)i;
+        n += __popc(mask);
+    }
+    n_cyl_out = n;
+    const int n_rest = ob.n_box + ob.n_sph + ob.n_obox + ob.n_tri;
+    for (int base = 0; base < n_rest; base += 32) {
+        int i = base + (int)lane;
+        bool keep = false;
+        if (i < n_rest) {
+            keep = !b.ok;
+            if (b.ok) {
+                int id = i;
+                if (id < ob.n_box) {
+                    const float* c = ob.box + BOX_STRIDE * id;
+                    const V3 lo = v3(c[0], c[1], c[2]), hi = v3(c[3], c[4], c[5]);
+                    const V3 hd = 0.5f * (hi - lo);
+                    keep = beam_keeps_ball(b, 0.5f * (lo + hi), sqrtf(dot(hd, hd)) * 1.0001f);
+                } else if ((id -= ob.n_box) < ob.n_sph) {
+                    const float* c = ob.sph + SPH_STRIDE * id;
+                    keep = beam_keeps_ball(b, v3(c[0], c[1], c[2]), fabsf(c[3]));
+                } else if ((id -= ob.n_sph) < ob.n_obox) {
+                    const float* c = ob.obox + OBOX_STRIDE * id;
+                    keep = beam_keeps_ball(b, v3(c[0], c[1], c[2]), sqrtf(c[3] * c[3] + c[4] * c[4] + c[5] * c[5]) * 1.0001f);
+                } else {
+                    id -= ob.n_obox;
+                    const float* c = ob.tri + TRI_STRIDE * id;
+                    const V3 v0 = v3(c[0], c[1], c[2]), v1 = v3(c[3], c[4], c[5]), v2 = v3(c[6], c[7], c[8]);
+                    const V3 m = 0.33333334f * (v0 + v1 + v2);
+                    const V3 d0 = v0 - m, d1 = v1 - m, d2 = v2 - m;
+                    keep = beam_keeps_ball(b, m, sqrtf(fmaxf(dot(d0, d0), fmaxf(dot(d1, d1), dot(d2, d2)))) * 1.0001f);
+                }
+            }
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) list[n + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)(ob.n_cyl + i);
+        n += __popc(mask);
+    }
+    __syncwarp();
+    return n;
+}
+
+// ---------------------------------------------------------------- binning
+// Soft (Gaussian-splat) sensors: DifferentiableHexagonalSensor.accumulate (hexagonal.py:264-314)
+template <typename LUT>
+__device__ __forceinline__ void splat_soft_hex(const SensDev& se, const LUT* lut, float x, float y, float val, float* hist) {
+    float xg, yg; hex_grid_coords(se, x, y, xg, yg);
+    const float q = (0.5773502691896257f * xg - yg / 3.0f) / se.size, r = (2.0f * yg / 3.0f) / se.size;
+    float qb, rb; hex_round(q, r, qb, rb);
+    if (!(fabsf(qb) < 1e6f && fabsf(rb) < 1e6f)) return;
+    const float ddx = xg - se.size_sqrt3 * (qb + rb / 2.0f), ddy = yg - se.size_1p5 * rb;
+    const int K = se.ksize;
+    const float inv_sigma = 1.0f / se.sigma;
+    float wsum = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int oq = -K; oq <= K; ++oq)
+            for (int orr = -K; orr <= K; ++orr) {
+                if (max(max(abs(oq), abs(orr)), abs(oq + orr)) > K) continue;
+                const float ox = se.size_sqrt3 * ((float)oq + (float)orr / 2.0f), oy = se.size_1p5 * (float)orr;
+                const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
+                const float hd = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) / se.inradius;
+                const float z = hd * inv_sigma;
+                const float w = expf(-0.5f * z * z);
+                if (pass == 0) { wsum += w; continue; }
+                const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
+                if (pix >= 0) atomicAdd(hist + pix, val * (w / wsum));
+            }
+    }
+}
+
+// DifferentiableSquareSensor.accumulate (square.py:144-172)
+__device__ __forceinline__ void splat_soft_square(const SensDev& se, float x, float y, float val, float* img) {
+    const float xp = (x - se.x0) / se.dx, yp = (y - se.y0) / se.dy;
+    const float xb = floorf(xp), yb = floorf(yp);
+    const int K = se.ksize;
+    if (!(xb >= (float)(-K - 1) && xb <= (float)(se.W + K) && yb >= (float)(-K - 1) && yb <= (float)(se.H + K))) return;
+    const float fx = xp - xb, fy = yp - yb;
+    const float inv_s2 = 1.0f / (se.sigma * se.sigma);
+    float wsum = 0.f;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int oy = -K; oy <= K; ++oy)
+            for (int ox = -K; ox <= K; ++ox) {
+                const float dx = fx - (float)ox, dy = fy - (float)oy;
+                const float w = expf(-0.5f * (dx * dx + dy * dy) * inv_s2);
+                if (pass == 0) { wsum += w; continue; }
+                const int xi = (int)xb + ox, yi = (int)yb + oy;
+                if (xi >= 0 && xi < se.W && yi >= 0 && yi < se.H) atomicAdd(img + (size_t)yi * se.W + xi, val * (w / wsum));
+            }
+}
+
+// ---------------------------------------------------------------- the kernel
+template <int SRC, int SENS, int MODE, bool STAGES>
+__global__ void __launch_bounds__(256)
+trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
+             const LaunchPlan plan, float* __restrict__ out, float* __restrict__ out_val, int* __restrict__ out_pix) {
+    extern __shared__ __align__(16) float smem[];
+    ObsSmem ob;
+    stage_obstructions(sc, smem, ob);
+    const int n_obs = sc.n_cyl + sc.n_box + sc.n_sph + sc.n_obox + sc.n_tri;
+    float* p = smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri);
+    float* hist = nullptr;
+    const short* lut = nullptr;
+    if (SENS == SENS_HEX) {
+        if (MODE != MODE_DEBUG) { hist = p; p += sc.sens.npix; }
+        short* l = reinterpret_cast<short*>(p);
+        for (int i = threadIdx.x; i < sc.sens.tq * sc.sens.tr; i += blockDim.x) l[i] = (short)sc.sens.lookup[i];
+        lut = l;
+        p += (sc.sens.tq * sc.sens.tr + 1) / 2;
+        if (hist) for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) hist[i] = 0.f;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    unsigned short* list = sc.cull ? reinterpret_cast<unsigned short*>(p) + (size_t)warp * ((n_obs + 1) & ~1) : nullptr;
+    __syncthreads();
+
+    const int M = sc.M;
+    const bool soft = sc.sens.kind >= IACT_SENSOR_SOFT_SQUARE;
+    const size_t npix = SENS == SENS_HEX ? (size_t)sc.sens.npix : (size_t)sc.sens.W * sc.sens.H;
+
+    for (long long item = blockIdx.x; item < plan.n_items; item += gridDim.x) {
+        const int s = (int)(item / plan.n_chunks), ch = (int)(item - (long long)s * plan.n_chunks);
+        const int f0 = ch * plan.chunk_facets, f1 = min(sc.F, f0 + plan.chunk_facets);
+        const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
+        const float sval = __ldg(values + s);
+        float* gout = MODE == MODE_MATRIX ? out + (size_t)s * npix : out;
+
+        const int n_w = (f1 - f0) * plan.msplit;
+        for (int wi = warp; wi < n_w; wi += nwarps) {
+            const int fi = wi / plan.msplit, part = wi - fi * plan.msplit;
+            const int f = f0 + fi;
+            const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
+            int n_list = 0, n_list_cyl = 0;
+            if (list) {
+                const Beam beam = make_beam<SRC>(__ldg(sc.bounds + f), src);
+                n_list = build_list(ob, beam, list, n_list_cyl);
+            }
+            const float4* tab = sc.world + ((size_t)f * M) * 2;
+            for (int m = m0 + lane; m < m1; m += 32) {
+                const float4 a = __ldg(tab + 2 * m), b = __ldg(tab + 2 * m + 1);
+                V3 o = v3(a.x, a.y, a.z);
+                const V3 n = v3(b.x, b.y, b.z);
+                // render.py:129-133
+                V3 d;
+                if (SRC == IACT_SOURCE_POINT) {
+                    d = o - src;
+                    const float nrm = sqrtf(dot(d, d));
+                    d = v3(d.x / nrm, d.y / nrm, d.z / nrm);
+                } else {
+                    d = src;
+                }
+                // render.py:138 shadow of the incoming leg (infinite ray back towards the source)
+                const bool blocked = occluded(ob, o, -d, list, n_list_cyl, n_list);
+                // render.py:140-141, reflection.py:17-19
+                const float c = dot(d, n);
+                d = d - (2.0f * c) * n;
+                float val = blocked ? 0.f : (sval * (-c)) / a.w;
+                if (STAGES) {
+                    for (int st = 0; st < sc.n_stages; ++st) reflect_at_stage(sc.stages[st], ob, o, d, val);
+                }
+                // render.py:152-155
+                float x, y;
+                plane_hit(sc.sens, o, d, x, y);
+                if (MODE == MODE_DEBUG) {
+                    const size_t ri = ((size_t)f * plan.S + s) * M + m;
+                    out[2 * ri] = x; out[2 * ri + 1] = y; out_val[ri] = val;
+                    if (out_pix) {
+                        int pix = -1;
+                        if (!soft) pix = SENS == SENS_HEX ? hex_pixel(sc.sens, lut, x, y) : square_pixel(sc.sens, x, y);
+                        out_pix[ri] = pix;
+                    }
+                } else if (val != 0.f) {
+                    if (SENS == SENS_HEX) {
+                        if (soft) splat_soft_hex(sc.sens, lut, x, y, val, hist);
+                        else { const int pix = hex_pixel(sc.sens, lut, x, y); if (pix >= 0) atomicAdd(hist + pix, val); }
+                    } else {
+                        if (soft) splat_soft_square(sc.sens, x, y, val, gout);
+                        else { const int pix = square_pixel(sc.sens, x, y); if (pix >= 0) atomicAdd(gout + pix, val); }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (MODE == MODE_MATRIX && SENS == SENS_HEX) {
+            __syncthreads();
+            if (plan.n_chunks == 1) {
+                for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) { gout[i] = hist[i]; hist[i] = 0.f; }
+            } else {
+                for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) {
+                    const float v = hist[i];
+                    if (v != 0.f) { atomicAdd(gout + i, v); hist[i] = 0.f; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (MODE == MODE_RENDER && SENS == SENS_HEX) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) {
+            const float v = hist[i];
+            if (v != 0.f) atomicAdd(out + i, v);
+        }
+    }
+}
+
+// sensor.accumulate on free-standing hits: one thread per hit, red.global into the image.
+__global__ void __launch_bounds__(256) accumulate_kernel(const SensDev se, const float* __restrict__ x, const float* __restrict__ y,
+                                                         const float* __restrict__ v, long long n, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float val = v[i];
+    switch (se.kind) {
+        case IACT_SENSOR_SQUARE: { const int p = square_pixel(se, x[i], y[i]); if (p >= 0) atomicAdd(out + p, val); break; }
+        case IACT_SENSOR_HEX:    { const int p = hex_pixel(se, se.lookup, x[i], y[i]); if (p >= 0) atomicAdd(out + p, val); break; }
+        case IACT_SENSOR_SOFT_SQUARE: splat_soft_square(se, x[i], y[i], val, out); break;
+        default: splat_soft_hex(se, se.lookup, x[i], y[i], val, out); break;
+    }
+}
+
+// ---------------------------------------------------------------- host side
+int g_sm_count = 0;
+
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+void fill_sensor(const IactSensor& s, SensDev& d) {
+    memset(&d, 0, sizeof(d));
+    d.kind = s.kind;
+    // euler_to_matrix (transforms.py:72-106) in float32
+    const float D2R = 0.017453292519943295f;
+    const float rx = s.euler[0] * D2R, ry = s.euler[1] * D2R, rz = s.euler[2] * D2R;
+    const float cx = cosf(rx), sx = sinf(rx), cy = cosf(ry), sy = sinf(ry), cz = cosf(rz), sz = sinf(rz);
+    const float a[3][3] = {{cy, sy * sx, sy * cx}, {0.f, cx, -sx}, {-sy, cy * sx, cy * cx}};
+    float R[3][3];
+    for (int j = 0; j < 3; ++j) { R[0][j] = cz * a[0][j] - sz * a[1][j]; R[1][j] = sz * a[0][j] + cz * a[1][j]; R[2][j] = a[2][j]; }
+    for (int i = 0; i < 3; ++i) { d.pos[i] = s.position[i]; d.u1[i] = R[i][0]; d.u2[i] = R[i][1]; d.nrm[i] = R[i][2]; }
+    d.ndotp = d.nrm[0] * d.pos[0] + d.nrm[1] * d.pos[1] + d.nrm[2] * d.pos[2];
+    d.W = s.width; d.H = s.height;
+    d.x0 = (float)s.x0; d.y0 = (float)s.y0; d.dx = (float)s.dx; d.dy = (float)s.dy; d.edge = (float)s.edge_width;
+    d.goffx = (float)s.grid_offset[0]; d.goffy = (float)s.grid_offset[1];
+    const float ang = (float)(-s.grid_rotation);
+    d.cr = cosf(ang); d.sr = sinf(ang);
+    d.size = (float)s.hex_size; d.size_sqrt3 = (float)(s.hex_size * 1.7320508075688772);
+    d.size_1p5 = (float)(s.hex_size * 1.5); d.inradius = (float)s.hex_inradius;
+    d.edge_thr = s.hex_inradius != 0.0 ? (float)(1.0 - s.edge_width / s.hex_inradius) : 1.0f;
+    d.qmin = s.q_min; d.rmin = s.r_min; d.tq = s.table_q; d.tr = s.table_r; d.npix = s.n_pixels;
+    d.lookup = s.lookup; d.sigma = (float)s.sigma; d.ksize = s.kernel_size;
+}
+
+int fill_scene(const IactScene* s, SceneDev& d) {
+    IACT_REQUIRE(s, "null scene");
+    IACT_REQUIRE(s->n_facets >= 0 && s->n_samples >= 0, "negative facet/sample count");
+    IACT_REQUIRE(s->n_facets == 0 || s->n_samples == 0 || (s->world && s->bounds), "null world table");
+    IACT_REQUIRE(s->n_stages >= 0 && s->n_stages <= IACT_MAX_STAGES, "too many optical stages");
+    IACT_REQUIRE(s->n_cyl >= 0 && s->n_box >= 0 && s->n_sph >= 0 && s->n_obox >= 0 && s->n_tri >= 0, "negative obstruction count");
+    IACT_REQUIRE((long long)s->n_cyl + s->n_box + s->n_sph + s->n_obox + s->n_tri < 65535, "too many obstructions (max 65534)");
+    memset(&d, 0, sizeof(d));
+    d.F = s->n_facets; d.M = s->n_samples;
+    d.world = reinterpret_cast<const float4*>(s->world); d.bounds = reinterpret_cast<const float4*>(s->bounds);
+    d.n_cyl = s->n_cyl; d.cyl_p1 = s->cyl_p1; d.cyl_p2 = s->cyl_p2; d.cyl_r = s->cyl_r;
+    d.n_box = s->n_box; d.box_p1 = s->box_p1; d.box_p2 = s->box_p2;
+    d.n_sph = s->n_sph; d.sph_c = s->sph_c; d.sph_r = s->sph_r;
+    d.n_obox = s->n_obox; d.obox_c = s->obox_c; d.obox_h = s->obox_h; d.obox_R = s->obox_R;
+    d.n_tri = s->n_tri; d.tri_v0 = s->tri_v0; d.tri_v1 = s->tri_v1; d.tri_v2 = s->tri_v2;
+    IACT_REQUIRE(!d.n_cyl || (d.cyl_p1 && d.cyl_p2 && d.cyl_r), "null cylinder table");
+    IACT_REQUIRE(!d.n_box || (d.box_p1 && d.box_p2), "null box table");
+    IACT_REQUIRE(!d.n_sph || (d.sph_c && d.sph_r), "null sphere table");
+    IACT_REQUIRE(!d.n_obox || (d.obox_c && d.obox_h && d.obox_R), "null oriented-box table");
+    IACT_REQUIRE(!d.n_tri || (d.tri_v0 && d.tri_v1 && d.tri_v2), "null triangle table");
+    d.n_stages = s->n_stages;
+    for (int i = 0; i < s->n_stages; ++i) {
+        d.stages[i].n = s->stages[i].n_mirrors; d.stages[i].rec = s->stages[i].records; d.stages[i].verts = s->stages[i].verts;
+        IACT_REQUIRE(d.stages[i].n >= 0 && (d.stages[i].n == 0 || d.stages[i].rec), "bad mirror stage");
+    }
+    const IactSensor& se = s->sensor;
+    IACT_REQUIRE(se.kind >= IACT_SENSOR_SQUARE && se.kind <= IACT_SENSOR_SOFT_HEX, "unknown sensor kind");
+    if (se.kind == IACT_SENSOR_SQUARE || se.kind == IACT_SENSOR_SOFT_SQUARE) {
+        IACT_REQUIRE(se.width > 0 && se.height > 0 && se.dx != 0.0 && se.dy != 0.0, "bad square sensor");
+    } else {
+        IACT_REQUIRE(se.n_pixels > 0 && se.n_pixels < 32768 && se.table_q > 0 && se.table_r > 0 && se.lookup && se.hex_size > 0.0,
+                     "bad hexagonal sensor (n_pixels must be < 32768)");
+    }
+    if (se.kind >= IACT_SENSOR_SOFT_SQUARE) IACT_REQUIRE(se.sigma > 0.0 && se.kernel_size >= 0 && se.kernel_size <= 8, "bad soft-sensor parameters");
+    fill_sensor(se, d.sens);
+    d.cull = s->cull;
+    return IACT_OK;
+}
+
+size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
+    const int n_obs = d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri;
+    size_t fl = obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri);
+    if (sens == SENS_HEX) {
+        if (mode != MODE_DEBUG) fl += d.sens.npix;
+        fl += (d.sens.tq * d.sens.tr + 1) / 2;
+    }
+    size_t bytes = fl * 4;
+    if (d.cull) bytes += (size_t)nwarps * ((n_obs + 1) & ~1) * 2;
+    return bytes + 16;
+}
+
+template <int SRC, int SENS, int MODE, bool STAGES>
+int launch_variant(const SceneDev& d, const float* sources, const float* values, const LaunchPlan& plan,
+                   float* out, float* out_val, int* out_pix, cudaStream_t stream) {
+    const int threads = 256;
+    const size_t smem = smem_bytes(d, SENS, MODE, threads / 32);
+    if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
+    auto kern = trace_kernel<SRC, SENS, MODE, STAGES>;
+    if (smem > 48 * 1024) IACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    IACT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    if (occ < 1) occ = 1;
+    const long long max_blocks = (long long)sm_count() * occ;
+    const unsigned grid = (unsigned)std::max(1LL, std::min(plan.n_items, max_blocks));
+    kern<<<grid, threads, smem, stream>>>(d, sources, values, plan, out, out_val, out_pix);
+    iact_count_launch();
+    return iact_check_cuda(cudaGetLastError(), "trace_kernel launch");
+}
+
+template <int SRC, int SENS, int MODE>
+int launch_stages(const SceneDev& d, const float* a, const float* b, const LaunchPlan& p, float* o, float* ov, int* op, cudaStream_t st) {
+    return d.n_stages > 0 ? launch_variant<SRC, SENS, MODE, true>(d, a, b, p, o, ov, op, st)
+                          : launch_variant<SRC, SENS, MODE, false>(d, a, b, p, o, ov, op, st);
+}
+template <int SRC, int MODE>
+int launch_sens(const SceneDev& d, const float* a, const float* b, const LaunchPlan& p, float* o, float* ov, int* op, cudaStream_t st) {
+    const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
+    return hex ? launch_stages<SRC, SENS_HEX, MODE>(d, a, b, p, o, ov, op, st)
+               : launch_stages<SRC, SENS_SQUARE, MODE>(d, a, b, p, o, ov, op, st);
+}
+template <int MODE>
+int launch_src(int source_type, const SceneDev& d, const float* a, const float* b, const LaunchPlan& p, float* o, float* ov, int* op, cudaStream_t st) {
+    return source_type == IACT_SOURCE_POINT ? launch_sens<IACT_SOURCE_POINT, MODE>(d, a, b, p, o, ov, op, st)
+                                            : launch_sens<IACT_SOURCE_PARALLEL, MODE>(d, a, b, p, o, ov, op, st);
+}
+
+// Split S x F x M rays into block items (source, facet chunk) and warp items (facet, sample range).
+LaunchPlan make_plan(const SceneDev& d, int S, int mode) {
+    LaunchPlan p;
+    p.S = S;
+    const long long target = (long long)sm_count() * 16;          // block items wanted for balance
+    int n_chunks = 1;
+    if (S < target) n_chunks = (int)std::min<long long>(d.F, (target + S - 1) / std::max(S, 1));
+    const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
+    if (mode == MODE_MATRIX && hex && S >= 2 * sm_count()) n_chunks = 1;   // plain-store flush, no atomics
+    n_chunks = std::max(n_chunks, 1);
+    p.chunk_facets = (d.F + n_chunks - 1) / n_chunks;
+    p.n_chunks = (d.F + p.chunk_facets - 1) / p.chunk_facets;
+    // keep >= 16 warp items per block item when the chunk is short
+    p.msplit = 1;
+    if (p.chunk_facets < 16) p.msplit = std::max(1, std::min((16 + p.chunk_facets - 1) / p.chunk_facets, (d.M + 63) / 64));
+    p.msize = ((d.M + p.msplit - 1) / p.msplit + 31) / 32 * 32;
+    p.msplit = (d.M + p.msize - 1) / std::max(p.msize, 1);
+    p.n_items = (long long)S * p.n_chunks;
+    return p;
+}
+
+int run(const IactScene* scene, const float* sources, const float* values, int S, int source_type, int mode,
+        float* out, float* out_val, int* out_pix, void* stream) {
+    SceneDev d;
+    int rc = fill_scene(scene, d);
+    if (rc) return rc;
+    IACT_REQUIRE(S >= 0, "negative source count");
+    IACT_REQUIRE(source_type == IACT_SOURCE_POINT || source_type == IACT_SOURCE_PARALLEL, "bad source_type");
+    IACT_REQUIRE(out, "null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
+    const size_t npix = hex ? (size_t)d.sens.npix : (size_t)d.sens.W * d.sens.H;
+    const bool empty = S == 0 || d.F == 0 || d.M == 0;
+    if (!empty) IACT_REQUIRE(sources && values, "null sources/values");
+    LaunchPlan plan = make_plan(d, std::max(S, 1), mode);
+    if (mode == MODE_RENDER) {
+        IACT_CUDA(cudaMemsetAsync(out, 0, npix * sizeof(float), st));        // render.py:198-199,218
+    } else if (mode == MODE_MATRIX) {
+        if (empty || !(hex && plan.n_chunks == 1)) IACT_CUDA(cudaMemsetAsync(out, 0, (size_t)S * npix * sizeof(float), st));
+    } else {
+        IACT_REQUIRE(out_val, "null out_val");
+    }
+    if (empty) return IACT_OK;
+    plan.S = S;
+    plan.n_items = (long long)S * plan.n_chunks;
+    switch (mode) {
+        case MODE_RENDER: return launch_src<MODE_RENDER>(source_type, d, sources, values, plan, out, out_val, out_pix, st);
+        case MODE_MATRIX: return launch_src<MODE_MATRIX>(source_type, d, sources, values, plan, out, out_val, out_pix, st);
+        default:          return launch_src<MODE_DEBUG>(source_type, d, sources, values, plan, out, out_val, out_pix, st);
+    }
+}
+
+}  // namespace
+
+extern "C" int iact_accumulate(const IactSensor* sensor, const float* x, const float* y, const float* values,
+                               long long n, float* out, void* stream) {
+    IACT_REQUIRE(sensor && out && n >= 0, "bad arguments");
+    IACT_REQUIRE(n == 0 || (x && y && values), "null input");
+    IactScene tmp;
+    memset(&tmp, 0, sizeof(tmp));
+    tmp.sensor = *sensor;
+    SceneDev d;
+    int rc = fill_scene(&tmp, d);
+    if (rc) return rc;
+    const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
+    const size_t npix = hex ? (size_t)d.sens.npix : (size_t)d.sens.W * d.sens.H;
+    cudaStream_t st = (cudaStream_t)stream;
+    IACT_CUDA(cudaMemsetAsync(out, 0, npix * sizeof(float), st));
+    if (n == 0) return IACT_OK;
+    accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.sens, x, y, values, n, out);
+    iact_count_launch();
+    return iact_check_cuda(cudaGetLastError(), "accumulate_kernel launch");
+}
+
+extern "C" int iact_render(const IactScene* scene, const float* sources, const float* values, int n_sources,
+                           int source_type, float* out_image, void* stream) {
+    return run(scene, sources, values, n_sources, source_type, MODE_RENDER, out_image, nullptr, nullptr, stream);
+}
+
+extern "C" int iact_response_matrix(const IactScene* scene, const float* sources, const float* values, int n_sources,
+                                    int source_type, float* out_matrix, void* stream) {
+    return run(scene, sources, values, n_sources, source_type, MODE_MATRIX, out_matrix, nullptr, nullptr, stream);
+}
+
+extern "C" int iact_render_debug(const IactScene* scene, const float* sources, const float* values, int n_sources,
+                                 int source_type, float* out_xy, float* out_val, int32_t* out_pixel, void* stream) {
+    return run(scene, sources, values, n_sources, source_type, MODE_DEBUG, out_xy, out_val, out_pixel, stream);
+}

@@ -1,0 +1,4 @@
+from .yaml_loader import load_telescope, build_telescope
+from .scene_pack import pack_config, unpack_config, load_packed_config, packaged_config
+
+__all__ = ["load_telescope", "build_telescope", "pack_config", "unpack_config", "load_packed_config", "packaged_config"]

@@ -1,0 +1,111 @@
+"""Test helpers: product Telescope -> oracle scene dict, synthetic scenes, comparison utilities."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import scene as oscene
+
+
+def _np(t):
+    return t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
+
+
+def sensor_to_oracle(s):
+    from iactrace_b200.sensors import (DifferentiableHexagonalSensor, DifferentiableSquareSensor, HexagonalSensor,
+                                       SquareSensor)
+    if isinstance(s, HexagonalSensor):
+        hard = oscene.make_hex_sensor(_np(s.position), _np(s.rotation), _np(s.hex_centers), s.edge_width,
+                                      grid=s.grid_constants())
+        if isinstance(s, DifferentiableHexagonalSensor):
+            return oscene.make_soft_hex_sensor(hard, s.sigma, s.kernel_size)
+        return hard
+    if isinstance(s, SquareSensor):
+        bounds = (s.x0, s.x0 + s.dx * s.width, s.y0, s.y0 + s.dy * s.height)
+        if isinstance(s, DifferentiableSquareSensor):
+            o = oscene.make_soft_square_sensor(_np(s.position), _np(s.rotation), s.width, s.height, bounds,
+                                               s.sigma, s.kernel_size)
+        else:
+            o = oscene.make_square_sensor(_np(s.position), _np(s.rotation), s.width, s.height, bounds, s.edge_width)
+        o.update(x0=s.x0, y0=s.y0, dx=s.dx, dy=s.dy)
+        return o
+    raise TypeError(type(s))
+
+
+def to_oracle_scene(tel):
+    """Oracle scene fed with the PRODUCT's sample tables (isolates tracing from sampling)."""
+    from iactrace_b200.core import obstructions as O
+    groups = []
+    for g in tel.mirror_groups:
+        d = dict(kind=g.kind, stage=g.optical_stage, positions=_np(g.positions), rotations=_np(g.rotations),
+                 offsets=_np(g.offsets), curvature=g.curvature, conic=g.conic, aspheric=np.asarray(g.aspheric),
+                 points=_np(g.points), normals=_np(g.normals), weights=_np(g.weights),
+                 delta=_np(g.perturbation_delta), scale=_np(g.perturbation_scale))
+        if g.kind == "disk":
+            d["radii"] = _np(g.radii)
+        else:
+            d["vertices"] = _np(g.vertices)
+        groups.append(d)
+    obs = []
+    for g in tel.obstruction_groups or []:
+        if isinstance(g, O.CylinderGroup):
+            obs.append(dict(type="cylinder", p1=_np(g.p1), p2=_np(g.p2), r=_np(g.r)))
+        elif isinstance(g, O.BoxGroup):
+            obs.append(dict(type="box", p1=_np(g.p1), p2=_np(g.p2)))
+        elif isinstance(g, O.SphereGroup):
+            obs.append(dict(type="sphere", centers=_np(g.centers), radii=_np(g.radii)))
+        elif isinstance(g, O.OrientedBoxGroup):
+            obs.append(dict(type="oriented_box", centers=_np(g.centers), half_extents=_np(g.half_extents),
+                            rotations=_np(g.rotations)))
+        elif isinstance(g, O.TriangleGroup):
+            obs.append(dict(type="triangle", v0=_np(g.v0), v1=_np(g.v1), v2=_np(g.v2)))
+    return dict(name=tel.name, groups=groups, obstructions=obs, sensors=[sensor_to_oracle(s) for s in tel.sensors])
+
+
+def subset_config(cfg, n_mirrors=None, mirror_step=1):
+    """A smaller telescope: every ``mirror_step``-th mirror, at most ``n_mirrors``."""
+    c = dict(cfg)
+    m = cfg["mirrors"][::mirror_step]
+    c["mirrors"] = m[:n_mirrors] if n_mirrors else m
+    return c
+
+
+def cassegrain_config(with_obstructions=True):
+    """The two-mirror telescope of the reference's examples/Cassegrain.ipynb cell 3, as a YAML-style
+    config dict, plus BASELINE.md's synthetic obstructions (config 3)."""
+    mirrors = []
+    for ang in (0, 60, 120, 180, 240, 300):
+        a = np.radians(ang)
+        x, y = float(2.0 * np.cos(a)), float(2.0 * np.sin(a))
+        mirrors.append(dict(id=f"P{ang}", template="primary", position=[x, y, 0.0], orientation=[0.0, 0.0, 0.0],
+                            aperture=dict(type="circular", radius=1.0), offset=[x, y], stage=0))
+    mirrors.append(dict(id="S", template="secondary", position=[0.0, 0.0, 6.0], orientation=[180.0, 0.0, 0.0],
+                        aperture=dict(type="circular", radius=1.0), offset=[0.0, 0.0], stage=1))
+    obs = []
+    if with_obstructions:
+        for (a, b) in (((0.9, 0, 6.2), (3.2, 0, 0.3)), ((-0.9, 0, 6.2), (-3.2, 0, 0.3)),
+                       ((0, 0.9, 6.2), (0, 3.2, 0.3)), ((0, -0.9, 6.2), (0, -3.2, 0.3))):
+            obs.append(dict(type="cylinder", p1=list(map(float, a)), p2=list(map(float, b)), r=0.03))
+        obs.append(dict(type="box", p1=[3.3, -0.3, 0.0], p2=[3.9, 0.3, 0.8]))
+        obs.append(dict(type="sphere", center=[-3.6, 0.0, 0.5], r=0.3))
+    return dict(telescope=dict(name="test_cassegrain", units="m"),
+                mirror_templates=dict(primary=dict(surface=dict(curvature=0.05, conic=-1.0, aspheric=[])),
+                                      secondary=dict(surface=dict(curvature=-0.05, conic=-1.0, aspheric=[]))),
+                mirrors=mirrors, obstructions=obs,
+                sensors=[dict(type="square", position=[0.0, 0.0, -0.45], orientation=[0.0, 0.0, 0.0], width=1024,
+                              height=1024, bounds=[-0.5, 0.5, -0.5, 0.5])])
+
+
+def point_grid(n_side, half_deg, dist=1e10):
+    """BASELINE.md config 2 sources: n_side^2 point sources on a grid of field angles."""
+    th = np.deg2rad(np.linspace(-half_deg, half_deg, n_side))
+    tx, ty = np.meshgrid(th, th, indexing="xy")
+    return np.stack([dist * np.tan(tx).ravel(), dist * np.tan(ty).ravel(), np.full(tx.size, dist)], 1).astype(np.float32)
+
+
+def parallel_grid(n_side, fov_deg):
+    """ResponseMatrix.ipynb cell 9 directions."""
+    fov = np.float32(fov_deg * np.pi / 180)
+    x1 = np.linspace(-fov / 2, fov / 2, n_side, dtype=np.float32)
+    X, Y = np.meshgrid(x1, x1, indexing="xy")
+    d = np.stack([X.ravel(), Y.ravel(), -np.ones(n_side * n_side, np.float32)], 1).astype(np.float32)
+    return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)

@@ -1,0 +1,206 @@
+"""Parity of the CUDA trace path (through the C ABI) against the oracle on identical inputs.
+
+Tolerances: float32 path; per-ray hit coordinates within 2e-5 m (f32 rounding of ~15-36 m lever
+arms), per-ray values within 1e-5 relative; images within 1e-4 relative per pixel (BASELINE.json)
+on pixels not touched by rays that sit within rounding noise of a pixel edge or a shadow edge;
+pixel indices bit-exact for rays farther than 1e-5 m from any pixel edge.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import iactrace_b200 as I
+from iactrace_b200.core import render as Rm
+from iactrace_b200.core import render, render_debug, render_response_matrix
+from iactrace_b200.io import build_telescope, load_packed_config
+from oracle import trace as otrace
+from _bridge import to_oracle_scene, subset_config, point_grid, parallel_grid
+
+EDGE_MARGIN = 1e-5   # metres
+
+
+def _tel(name, n_samples, step=1, n_mirrors=None, seed=0):
+    cfg = subset_config(load_packed_config(name), n_mirrors=n_mirrors, mirror_step=step)
+    return build_telescope(cfg, I.MCIntegrator(n_samples), I.random.key(seed))
+
+
+def _compare_rays(tel, src, val, stype, sensor_idx, xy_tol=2e-5):
+    osc = to_oracle_scene(tel)
+    xy, v, pix = render_debug(tel, src, val, stype, sensor_idx, return_pixels=True)
+    xy, v, pix = xy.cpu().numpy(), v.cpu().numpy(), pix.cpu().numpy()
+    oxy, ov = otrace.render_debug(osc, src, val, stype, sensor_idx, np.float64)
+    assert xy.shape == oxy.shape and v.shape == ov.shape
+    # shadow decisions: allow only grazing rays to differ
+    lit, olit = v != 0, ov != 0
+    flips = lit != olit
+    assert flips.mean() < 2e-4, f"{flips.sum()} shadow flips of {flips.size}"
+    both = lit & olit
+    np.testing.assert_allclose(v[both], ov[both], rtol=1e-5)
+    ok = both & (np.abs(oxy[:, 0]) < 1e9)
+    assert np.abs(xy[ok] - oxy[ok]).max() < xy_tol
+    # pixel index: bit-exact away from edges
+    s = osc["sensors"][sensor_idx]
+    oidx, ovalid, edge = otrace.pixel_index(s, oxy[:, 0], oxy[:, 1], np.float64)
+    opix = np.where(ovalid, oidx, -1)
+    if s["type"] == "hexagonal":
+        inr = s["hex_inradius"]
+        thr = 1.0 - s["edge_width"] / inr
+        near = (np.abs(edge - thr) * inr < EDGE_MARGIN) | (np.abs(edge - 1.0) * inr < EDGE_MARGIN)
+    else:
+        near = (np.abs(edge - s["edge_width"]) < EDGE_MARGIN) | (edge < EDGE_MARGIN)
+    chk = ok & ~near
+    assert np.array_equal(pix[chk], opix[chk]), f"{(pix[chk] != opix[chk]).sum()} pixel mismatches away from edges"
+    return dict(xy=xy, v=v, pix=pix, oxy=oxy, ov=ov, opix=opix, ambiguous=(ok & near) | flips, osc=osc)
+
+
+def _compare_image(img, r, shape, rtol=1e-4):
+    """CUDA image vs f64 oracle accumulation; pixels touched by ambiguous rays are excluded."""
+    npx = int(np.prod(shape))
+    oimg = np.bincount(r["opix"][r["opix"] >= 0], weights=r["ov"][r["opix"] >= 0], minlength=npx)
+    tainted = np.zeros(npx, bool)
+    for arr in (r["pix"], r["opix"]):
+        a = arr[r["ambiguous"]]
+        tainted[a[a >= 0]] = True
+    got = img.reshape(-1).astype(np.float64)
+    clean = ~tainted
+    assert clean.mean() > 0.9
+    np.testing.assert_allclose(got[clean], oimg[clean], rtol=rtol, atol=1e-7 * max(oimg.max(), 1e-30))
+    # and the image must equal the binning of the kernel's own per-ray output everywhere
+    own = np.bincount(r["pix"][r["pix"] >= 0], weights=r["v"][r["pix"] >= 0].astype(np.float64), minlength=npx)
+    np.testing.assert_allclose(got, own, rtol=2e-5, atol=1e-7 * max(own.max(), 1e-30))
+    return oimg
+
+
+@pytest.mark.parametrize("sensor_idx", [0, 1])
+def test_ct3_config1_on_axis_point_source(sensor_idx):
+    """BASELINE config 1: CT3, one on-axis point source at 1e10, MCIntegrator(1000), seed 0."""
+    tel = _tel("CT3", 1000)
+    src = np.array([[0.0, 0.0, 1e10]], np.float32)
+    val = np.ones(1, np.float32)
+    r = _compare_rays(tel, src, val, "point", sensor_idx)
+    img = render(tel, src, val, "point", sensor_idx).cpu().numpy()
+    assert img.shape == tuple(tel.sensors[sensor_idx].get_accumulator_shape())
+    _compare_image(img, r, img.shape)
+    if sensor_idx == 1:
+        # SURVEY section 4 anchor: ~100.7 m^2 shadowed effective area on the lid (MC noise ~0.3 %)
+        assert abs(img.sum() - 100.7) < 1.0
+
+
+@pytest.mark.parametrize("stype", ["point", "parallel"])
+@pytest.mark.parametrize("sensor_idx", [0, 2])
+def test_ct5_off_axis_grid(stype, sensor_idx):
+    """BASELINE config 2 geometry (CT5, off-axis grid) at a size the oracle finishes in seconds."""
+    tel = _tel("CT5", 23, step=11)
+    if stype == "point":
+        src = point_grid(3, 1.5)
+    else:
+        src = parallel_grid(3, 3.0)
+    val = np.linspace(0.5, 1.5, len(src)).astype(np.float32)
+    r = _compare_rays(tel, src, val, stype, sensor_idx, xy_tol=6e-5)
+    img = render(tel, src, val, stype, sensor_idx).cpu().numpy()
+    _compare_image(img, r, img.shape)
+
+
+def test_culling_is_exact():
+    """Conservative culling must not change a single ray: brute force and culled runs bit-identical."""
+    for name, stype, src in (("CT5", "point", point_grid(4, 1.5)), ("CT3", "parallel", parallel_grid(4, 5.5)),
+                             ("CT5", "point", np.array([[3.0, -2.0, 60.0], [0.0, 0.0, 36.0], [40.0, 5.0, 20.0]], np.float32))):
+        tel = _tel(name, 37, step=3)
+        val = np.ones(len(src), np.float32)
+        out = []
+        for cull in (True, False):
+            Rm.CULL_OBSTRUCTIONS = cull
+            try:
+                xy, v = render_debug(tel, src, val, stype, 0)
+                out.append((xy.cpu().numpy(), v.cpu().numpy()))
+            finally:
+                Rm.CULL_OBSTRUCTIONS = True
+        assert np.array_equal(out[0][1], out[1][1])
+        assert np.array_equal(out[0][0], out[1][0])
+        shadowed = (out[0][1] == 0).mean()
+        assert 0.0 < shadowed < 0.9
+
+
+def test_response_matrix_rows_are_single_source_images():
+    """BASELINE config 4 geometry: CT3 + roughness 24", parallel grid; row i == render of source i."""
+    tel = _tel("CT3", 16, step=4, seed=42).apply_roughness(24)
+    src = parallel_grid(5, 5.5)
+    val = np.ones(len(src), np.float32)
+    M = render_response_matrix(tel, src, val, "parallel", 0).cpu().numpy()
+    assert M.shape == (25, 960)
+    for i in (0, 7, 12, 24):
+        img = render(tel, src[i:i + 1], val[i:i + 1], "parallel", 0).cpu().numpy()
+        np.testing.assert_allclose(M[i], img, rtol=2e-6, atol=1e-9)
+    total = render(tel, src, val, "parallel", 0).cpu().numpy()
+    np.testing.assert_allclose(M.sum(0), total, rtol=2e-5, atol=1e-7)
+    # against the oracle's response matrix (f64), excluding nothing but using a looser per-pixel bound
+    oM = otrace.render_response_matrix(to_oracle_scene(tel), src, val, "parallel", 0, np.float64)
+    assert abs(M.sum() - oM.sum()) < 1e-3 * oM.sum()
+    # square sensor variant goes through the global-atomic path
+    Ms = render_response_matrix(tel, src[:3], val[:3], "parallel", 1)
+    assert Ms.shape == (3, 1024 * 1536)
+    img = render(tel, src[1:2], val[1:2], "parallel", 1).reshape(-1)
+    torch.testing.assert_close(Ms[1], img, rtol=2e-6, atol=1e-9)
+
+
+def test_many_sources_response_matrix_plain_store_path():
+    """S large enough that each block owns whole rows (no atomics, no memset)."""
+    tel = _tel("CT3", 8, step=16, seed=3)
+    src = parallel_grid(24, 5.5)
+    val = np.ones(len(src), np.float32)
+    out = torch.full((len(src), 960), float("nan"), device="cuda")
+    M = render_response_matrix(tel, src, val, "parallel", 0)
+    assert torch.isfinite(M).all()
+    total = render(tel, src, val, "parallel", 0)
+    torch.testing.assert_close(M.sum(0), total, rtol=1e-4, atol=1e-6)
+    del out
+
+
+def test_edge_cases():
+    tel = _tel("CT3", 4, n_mirrors=3)
+    # empty source list
+    img = render(tel, np.zeros((0, 3), np.float32), np.zeros((0,), np.float32), "point", 0)
+    assert img.shape == (960,) and float(img.abs().sum()) == 0.0
+    M = render_response_matrix(tel, np.zeros((0, 3), np.float32), np.zeros((0,), np.float32), "point", 0)
+    assert M.shape == (0, 960)
+    xy, v = render_debug(tel, np.zeros((0, 3), np.float32), np.zeros((0,), np.float32), "point", 0)
+    assert xy.shape == (0, 2) and v.shape == (0,)
+    # empty telescope -> zeros (render.py:198-199)
+    empty = I.Telescope([], [], tel.sensors)
+    assert float(render(empty, np.array([[0, 0, 1e10]], np.float32), np.ones(1, np.float32)).abs().sum()) == 0.0
+    # a source behind the dish: rays leave away from the camera -> sentinel hits, nothing binned
+    img = render(tel.clear_obstructions(), np.array([[0, 0, -1e10]], np.float32), np.ones(1, np.float32), "point", 0)
+    assert float(img.abs().sum()) == 0.0
+    # mismatched sources / values
+    with pytest.raises(ValueError):
+        render(tel, np.zeros((2, 3), np.float32), np.ones(3, np.float32))
+    # sensor index out of range
+    with pytest.raises(IndexError):
+        render(tel, np.zeros((1, 3), np.float32), np.ones(1, np.float32), "point", 5)
+    # unknown source_type strings mean 'parallel' (render.py:129-133)
+    d = np.array([[0.0, 0.0, -1.0]], np.float32)
+    a = render(tel, d, np.ones(1, np.float32), "parallel", 0)
+    b = render(tel, d, np.ones(1, np.float32), "anything", 0)
+    assert torch.equal(a, b)
+
+
+def test_torch_and_numpy_inputs_and_stream_ordering():
+    tel = _tel("CT3", 8, n_mirrors=6)
+    src = point_grid(2, 0.5)
+    val = np.ones(4, np.float32)
+    a = render(tel, src, val, "point", 0)
+    b = render(tel, torch.from_numpy(src).cuda(), torch.from_numpy(val).cuda(), "point", 0)
+    c = render(tel, src.astype(np.float64).tolist(), val.tolist(), "point", 0)
+    assert torch.equal(a, b) or torch.allclose(a, b, rtol=1e-6)
+    assert torch.allclose(a, c, rtol=1e-6)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        d = render(tel, src, val, "point", 0)
+    s.synchronize()
+    assert torch.allclose(a, d, rtol=1e-6)
+    # __call__ dispatch (telescope.py:56-83)
+    pts, vals = tel(src, val, "point", debug=True)
+    assert pts.shape == (6 * 4 * 8, 2) and vals.shape == (6 * 4 * 8,)
+    assert torch.allclose(tel(src, val), a, rtol=1e-6)
