@@ -1,0 +1,6 @@
+"""Runtime switches of the CUDA path (process-wide)."""
+
+# Conservative beam/obstruction culling in the trace kernel.  Culling never changes a ray's result
+# (tests/test_gpu_trace.py::test_culling_is_exact compares every ray against brute force); turning
+# it off exists for that test and for roofline comparisons.
+cull_obstructions = True

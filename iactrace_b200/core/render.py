@@ -13,10 +13,8 @@ import numpy as np
 import torch
 
 from .. import _native as N
+from .. import config
 from .._util import f32, contig
-
-# Conservative beam/obstruction culling (bit-identical per ray to brute force; tests flip it).
-CULL_OBSTRUCTIONS = True
 
 
 def _get_stages(mirror_groups):
@@ -151,7 +149,7 @@ def build_scene(tel, sensor_idx: int, keep: list, cull: bool | None = None):
         sc.stages[i].records = N.ptr(rec)
         sc.stages[i].verts = N.ptr(verts)
     sc.sensor = sensor._struct(keep)
-    sc.cull = int(CULL_OBSTRUCTIONS if cull is None else cull)
+    sc.cull = int(config.cull_obstructions if cull is None else cull)
     return sc, sensor
 
 

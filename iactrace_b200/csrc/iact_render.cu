@@ -278,6 +278,31 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     }
 }
 
+// Culling statistics: candidate-list lengths summed over all (facet, source) pairs.
+template <int SRC>
+__global__ void __launch_bounds__(256) cull_stats_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources,
+                                                         int S, unsigned long long* __restrict__ out) {
+    extern __shared__ __align__(16) float smem[];
+    ObsSmem ob;
+    stage_obstructions(sc, smem, ob);
+    const int n_obs = sc.n_cyl + sc.n_box + sc.n_sph + sc.n_obox + sc.n_tri;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    unsigned short* list = reinterpret_cast<unsigned short*>(smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri))
+                           + (size_t)warp * ((n_obs + 1) & ~1);
+    __syncthreads();
+    unsigned long long a = 0, b = 0, c = 0;
+    const long long n_pairs = (long long)sc.F * S;
+    for (long long i = (long long)blockIdx.x * nwarps + warp; i < n_pairs; i += (long long)gridDim.x * nwarps) {
+        const int f = (int)(i / S), s = (int)(i - (long long)f * S);
+        const V3 src = v3(sources[3 * s], sources[3 * s + 1], sources[3 * s + 2]);
+        int ncyl = 0;
+        const int n = build_list(ob, make_beam<SRC>(__ldg(sc.bounds + f), src), list, ncyl);
+        a += ncyl; b += n - ncyl; c += 1;
+        __syncwarp();
+    }
+    if (lane == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); atomicAdd(out + 2, c); }
+}
+
 // sensor.accumulate on free-standing hits: one thread per hit, red.global into the image.
 __global__ void __launch_bounds__(256) accumulate_kernel(const SensDev se, const float* __restrict__ x, const float* __restrict__ y,
                                                          const float* __restrict__ v, long long n, float* __restrict__ out) {
@@ -467,6 +492,28 @@ int run(const IactScene* scene, const float* sources, const float* values, int S
 }
 
 }  // namespace
+
+extern "C" int iact_cull_stats(const IactScene* scene, const float* sources, int n_sources, int source_type,
+                               unsigned long long* out3, void* stream) {
+    SceneDev d;
+    IactScene tmp = *scene;
+    tmp.cull = 1;
+    int rc = fill_scene(&tmp, d);
+    if (rc) return rc;
+    IACT_REQUIRE(sources && out3 && n_sources > 0 && d.F > 0, "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    IACT_CUDA(cudaMemsetAsync(out3, 0, 3 * sizeof(unsigned long long), st));
+    const size_t smem = smem_bytes(d, SENS_SQUARE, MODE_DEBUG, 8);
+    if (smem > 200 * 1024) { iact_set_error("scene too large for shared memory"); return IACT_ERR_UNSUPPORTED; }
+    auto launch = [&](auto kern) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<sm_count() * 4, 256, smem, st>>>(d, sources, n_sources, out3);
+    };
+    if (source_type == IACT_SOURCE_POINT) launch(cull_stats_kernel<IACT_SOURCE_POINT>);
+    else launch(cull_stats_kernel<IACT_SOURCE_PARALLEL>);
+    iact_count_launch();
+    return iact_check_cuda(cudaGetLastError(), "cull_stats_kernel launch");
+}
 
 extern "C" int iact_accumulate(const IactSensor* sensor, const float* x, const float* y, const float* values,
                                long long n, float* out, void* stream) {

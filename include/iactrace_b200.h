@@ -191,6 +191,12 @@ int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
                     const float* sources, const float* values, int n_sources, int source_type,
                     const float* cotangent, const IactGrads* grads, void* stream);
 
+/* Diagnostics for the roofline: candidate-list lengths of the conservative obstruction culling,
+ * summed over all (facet, source) pairs.  out3: device uint64[3] = {sum cylinders kept,
+ * sum other primitives kept, number of pairs}. */
+int iact_cull_stats(const IactScene* scene, const float* sources, int n_sources, int source_type,
+                    unsigned long long* out3, void* stream);
+
 /* Roofline probes (bench.py): dependent-free FP32 FMA throughput in FLOP/s written to
  * *out_flops, shared-memory float atomicAdd throughput in atomics/s to *out_atomics. */
 int iact_probe_fp32(int iters, double* out_flops, void* stream);

@@ -60,7 +60,7 @@ def test_all_obstruction_primitives():
     th = np.deg2rad(30.0)
     Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
     prims = {
-        "cylinder": [Cylinder([-6, 0.2, 5.0], [6, -0.1, 5.5], 0.25), Cylinder([2, 2, 0.5], [2, 2, 9], 0.4)],
+        "cylinder": [Cylinder([-6, 0.2, 5.0], [6, -0.1, 5.5], 0.25), Cylinder([2, 2, 0.5], [3.5, 1.0, 9], 0.4)],
         "box": [Box([-1.5, -1.0, 7.0], [1.0, 2.0, 7.4]), Box([3.0, 3.0, 2.0], [2.0, 4.5, 6.0])],
         "sphere": [Sphere([0.5, -2.0, 6.0], 1.1), Sphere([-3.0, 3.0, 4.0], 0.6)],
         "oriented_box": [OrientedBox([1.0, 1.0, 6.0], [1.5, 0.4, 0.3], Rz), OrientedBox([-3, -2, 5], [0.5, 0.5, 2], Rz.T)],

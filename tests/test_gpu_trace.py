@@ -12,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 import iactrace_b200 as I
-from iactrace_b200.core import render as Rm
+from iactrace_b200 import config as Rm
 from iactrace_b200.core import render, render_debug, render_response_matrix
 from iactrace_b200.io import build_telescope, load_packed_config
 from oracle import trace as otrace
@@ -111,12 +111,12 @@ def test_culling_is_exact():
         val = np.ones(len(src), np.float32)
         out = []
         for cull in (True, False):
-            Rm.CULL_OBSTRUCTIONS = cull
+            Rm.cull_obstructions = cull
             try:
                 xy, v = render_debug(tel, src, val, stype, 0)
                 out.append((xy.cpu().numpy(), v.cpu().numpy()))
             finally:
-                Rm.CULL_OBSTRUCTIONS = True
+                Rm.cull_obstructions = True
         assert np.array_equal(out[0][1], out[1][1])
         assert np.array_equal(out[0][0], out[1][0])
         shadowed = (out[0][1] == 0).mean()

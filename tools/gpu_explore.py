@@ -11,7 +11,7 @@ sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tests"))
 import iactrace_b200 as I
 from iactrace_b200 import _native as N
-from iactrace_b200.core import render as Rm
+from iactrace_b200 import config as Rm
 from iactrace_b200.core import render, render_response_matrix
 from iactrace_b200.io import build_telescope, load_packed_config
 from _bridge import point_grid, parallel_grid
@@ -47,10 +47,10 @@ def main():
             for cull in (True, False):
                 if not cull and M > 115:
                     continue
-                Rm.CULL_OBSTRUCTIONS = cull
+                Rm.cull_obstructions = cull
                 med, mn = timeit(lambda: render(tel, src, val, "point", sensor), n=3 if not cull else 5, warm=1)
                 print(f"CT5 render S=4096 M={M} sensor={sensor} cull={cull}: {med:.2f} ms  -> {rays/med/1e6:.1f} Grays/s")
-        Rm.CULL_OBSTRUCTIONS = True
+        Rm.cull_obstructions = True
     ct3 = load_packed_config("CT3")
     for M in (64, 1000):
         tel = build_telescope(ct3, I.MCIntegrator(M), I.random.key(42)).apply_roughness(24)
