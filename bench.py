@@ -272,11 +272,11 @@ def main():
         # candidate-list lengths actually tested per ray after exact culling
         keep = []
         sc, _ = build_scene(tel, w["sensor"], keep)
-        stats = torch.zeros(3, dtype=torch.int64, device=dev)
+        stats = torch.zeros(4, dtype=torch.int64, device=dev)
         N.check(N.lib().iact_cull_stats(sc, N.ptr(src_dev), len(src_np), 0 if stype == "point" else 1,
                                         stats.data_ptr(), None))
         torch.cuda.synchronize()
-        n_cyl_kept, n_oth_kept, n_pairs = [int(x) for x in stats.tolist()]
+        n_cyl_kept, n_oth_kept, n_pairs, n_lvl1 = [int(x) for x in stats.tolist()]
         sensor_kind = "hex" if hasattr(tel.sensors[w["sensor"]], "hex_size") else "square"
         n_cyl = sc.n_cyl
         n_oth = sc.n_box + sc.n_sph + sc.n_obox + sc.n_tri
@@ -291,7 +291,8 @@ def main():
                     "peak_source": "measured live: iact_probe_fp32 (dependent-free FFMA chains, all SMs); MEASURED_PEAKS.json has no FP32 CUDA-core figure",
                     "flops_per_ray": {"after_exact_culling": f_culled, "brute_force_reference": f_brute,
                                       "mean_cylinders_tested": n_cyl_kept / max(n_pairs, 1),
-                                      "mean_other_tested": n_oth_kept / max(n_pairs, 1)},
+                                      "mean_other_tested": n_oth_kept / max(n_pairs, 1),
+                                      "mean_level1_list": n_lvl1 / max(n_pairs, 1)},
                     "brute_force_equivalent_tflops": rays_per_step * f_brute / kern_s / 1e12,
                     "hbm": {"algorithmic_bytes_per_launch": out_bytes, "achieved_gbs": out_bytes / kern_s / 1e9,
                             "peak_gbs": _hbm_peak(), "note": "per-ray HBM bytes ~ 0: not the bound"}}

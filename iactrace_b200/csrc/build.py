@@ -34,6 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         return LIB
     nvcc = _nvcc()
     flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    flags += os.environ.get("IACT_NVCC_EXTRA", "").split()
     if verbose:
         flags += ["-Xptxas", "-v"]
 

@@ -1,15 +1,19 @@
-// K2/K3/K5: forward trace + sensor binning -- render, render_response_matrix, render_debug
-// (reference core/render.py:174-324, _trace_single_mirror :118-157).
+// K2/K3/K5/K7: forward trace + sensor binning -- render, render_response_matrix, render_debug
+// (reference core/render.py:174-324, _trace_single_mirror :118-157) with exact obstruction culling.
 //
 // Work decomposition:
 //   block item  = (source s, chunk of facets)      -> grid-stride over items
 //   warp item   = (facet f, sample range)          -> warps of the block stride over the chunk
 //   lane        = one ray (sample m of facet f seen from source s)
-// A warp first culls the obstruction tables against the (facet, source) beam into a per-warp
-// shared-memory candidate list (warp-uniform, conservative), then its lanes trace rays against
-// that short list.  Hex cameras are binned into a block-private shared-memory histogram that is
-// flushed once per source (response matrix: plain coalesced stores) or once per block (render:
-// one red.global per touched pixel); square cameras use red.global directly.
+// Culling is hierarchical and conservative (a primitive is dropped only if no ray of a beam can
+// touch it, with margins far above float32 rounding):
+//   level 1 (facet_cull_kernel, once per call): facet x all sources -> per-facet candidate list in HBM/L2
+//   level 2 (per warp item): (facet, source) beam against the facet list -> per-warp list in shared memory
+// Lanes then test their ray only against the warp's short list (warp-uniform loop).
+// Hex cameras are binned into a block-private shared-memory histogram with warp-aggregated adds
+// (one shared atomic per distinct pixel per warp), flushed once per source (response matrix: plain
+// coalesced stores) or once per block (render: one red.global per touched pixel); square cameras
+// use red.global directly.
 #include "iact_trace.cuh"
 #include <algorithm>
 #include <cstring>
@@ -24,14 +28,18 @@ struct LaunchPlan {
     long long n_items;
 };
 
-struct Beam { V3 c, u; float R, invD; bool ok; };
+// Level-1 culling output: per facet a list of primitive ids (cylinders first) and its two counts;
+// count.x < 0 means "no facet-level culling for this facet" (degenerate beam): use every primitive.
+struct FacetLists { const unsigned short* ids; const int2* count; int stride; };
 
-// Beam of all rays from the facet's bounding sphere towards the source (and beyond: the reference's
+struct Beam { V3 c, u; float R, invD, spread; bool ok; };
+
+// Beam of all rays from the facet's bounding sphere towards one source (and beyond: the reference's
 // shadow ray is infinite, render.py:138 + :40).
 template <int SRC>
 __device__ __forceinline__ Beam make_beam(float4 bnd, V3 src) {
     Beam b;
-    b.c = v3(bnd.x, bnd.y, bnd.z); b.R = bnd.w;
+    b.c = v3(bnd.x, bnd.y, bnd.z); b.R = bnd.w; b.spread = 0.f;
     V3 a = SRC == IACT_SOURCE_POINT ? src - b.c : -src;
     const float n2 = dot(a, a);
     b.ok = n2 > 1e-30f && n2 < 1e37f;
@@ -43,78 +51,118 @@ __device__ __forceinline__ Beam make_beam(float4 bnd, V3 src) {
 }
 
 // Conservative: false only if no ray of the beam can come within r of the segment [p1,p2].
+// A ray starts within R of c and its direction is within `spread` (chord) + 1.5708 R/D (point-source
+// parallax) of u; rays are half-lines, so everything behind the facet is out of reach.
 __device__ __forceinline__ bool beam_keeps_capsule(const Beam& b, V3 p1, V3 p2, float r) {
     const V3 a1 = p1 - b.c, a2 = p2 - b.c;
     const float t1 = dot(a1, b.u), t2 = dot(a2, b.u);
     const float tmx = fmaxf(t1, t2);
     const float marg = 2e-3f;
     if (tmx + r < -(b.R + marg)) return false;          // wholly behind every ray origin
-    const float tmax = 1.02f * (fmaxf(tmx, 0.f) + r + b.R);
-    const float Reff = b.R * (1.0f + 1.5708f * tmax * b.invD) + marg + 1e-5f * tmax;
+    const float tmax = 1.1f * (fmaxf(tmx, 0.f) + r + b.R);       // 1/cos(max beam half-angle 0.31 rad) < 1.1
+    const float Reff = b.R * (1.0f + 1.5708f * tmax * b.invD) + b.spread * tmax + marg + 1e-5f * tmax;
     const V3 q1 = a1 - t1 * b.u, q2 = a2 - t2 * b.u;
     const V3 e = q2 - q1;
     const float ee = dot(e, e);
-    const float s = ee > 1e-20f ? fminf(fmaxf(-dot(q1, e) / ee, 0.f), 1.f) : 0.f;
+    const float s = ee > 1e-20f ? fminf(fmaxf(-dot(q1, e) * frcp_fast(ee), 0.f), 1.f) : 0.f;
     const V3 dv = q1 + s * e;
     const float lim = Reff + r;
     return dot(dv, dv) <= lim * lim;
 }
-__device__ __forceinline__ bool beam_keeps_ball(const Beam& b, V3 m, float rho) {
-    return beam_keeps_capsule(b, m, m, rho);
+
+__device__ __forceinline__ bool keep_primitive(const ObsSmem& ob, const Beam& b, int id) {
+    if (id < ob.n_cyl) {
+        const float* c = ob.ccyl; const int n = ob.n_cyl;
+        return beam_keeps_capsule(b, v3(c[id], c[n + id], c[2 * n + id]), v3(c[3 * n + id], c[4 * n + id], c[5 * n + id]), c[6 * n + id]);
+    }
+    id -= ob.n_cyl;
+    const float* c = ob.cball; const int n = ob.n_rest;
+    const V3 m = v3(c[id], c[n + id], c[2 * n + id]);
+    return beam_keeps_capsule(b, m, m, c[3 * n + id]);
 }
 
-// Warp-cooperative compaction of the candidate primitives; returns total, sets n_cyl.
-__device__ __forceinline__ int build_list(const ObsSmem& ob, const Beam& b, unsigned short* list, int& n_cyl_out) {
+// Warp-cooperative compaction of the primitives a beam can reach.  `cand` (may be null = all
+// primitives) lists candidate ids, cylinders first (n_cand_cyl of n_cand).  Writes ids to `out`
+// (shared or global), returns the total and sets n_cyl_out.  Order is preserved.
+__device__ __forceinline__ int build_list(const ObsSmem& ob, const Beam& b, const unsigned short* cand, int n_cand_cyl,
+                                          int n_cand, unsigned short* out, int& n_cyl_out) {
     const unsigned lane = threadIdx.x & 31u;
-    int n = 0;
-    for (int base = 0; base < ob.n_cyl; base += 32) {
+    int n = 0, ncyl = 0;
+    for (int base = 0; base < n_cand; base += 32) {
         const int i = base + (int)lane;
         bool keep = false;
-        if (i < ob.n_cyl) {
-            const float* c = ob.cyl + CYL_STRIDE * i;
-            const V3 p1 = v3(c[0], c[1], c[2]);
-            keep = !b.ok || beam_keeps_capsule(b, p1, p1 + c[6] * v3(c[3], c[4], c[5]), c[7]);
+        int id = 0;
+        if (i < n_cand) {
+            id = cand ? (int)cand[i] : i;
+            keep = !b.ok || keep_primitive(ob, b, id);
         }
         const unsigned mask = __ballot_sync(0xffffffffu, keep);
-        if (keep) list[n + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)i;
+        if (keep) out[n + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)id;
         n += __popc(mask);
+        // cylinders come first in `cand`: count those kept among positions < n_cand_cyl
+        const int lim = n_cand_cyl - base;
+        ncyl += lim >= 32 ? __popc(mask) : (lim > 0 ? __popc(mask & ((1u << lim) - 1u)) : 0);
     }
-    n_cyl_out = n;
-    const int n_rest = ob.n_box + ob.n_sph + ob.n_obox + ob.n_tri;
-    for (int base = 0; base < n_rest; base += 32) {
-        int i = base + (int)lane;
-        bool keep = false;
-        if (i < n_rest) {
-            keep = !b.ok;
-            if (b.ok) {
-                int id = i;
-                if (id < ob.n_box) {
-                    const float* c = ob.box + BOX_STRIDE * id;
-                    const V3 lo = v3(c[0], c[1], c[2]), hi = v3(c[3], c[4], c[5]);
-                    const V3 hd = 0.5f * (hi - lo);
-                    keep = beam_keeps_ball(b, 0.5f * (lo + hi), sqrtf(dot(hd, hd)) * 1.0001f);
-                } else if ((id -= ob.n_box) < ob.n_sph) {
-                    const float* c = ob.sph + SPH_STRIDE * id;
-                    keep = beam_keeps_ball(b, v3(c[0], c[1], c[2]), fabsf(c[3]));
-                } else if ((id -= ob.n_sph) < ob.n_obox) {
-                    const float* c = ob.obox + OBOX_STRIDE * id;
-                    keep = beam_keeps_ball(b, v3(c[0], c[1], c[2]), sqrtf(c[3] * c[3] + c[4] * c[4] + c[5] * c[5]) * 1.0001f);
-                } else {
-                    id -= ob.n_obox;
-                    const float* c = ob.tri + TRI_STRIDE * id;
-                    const V3 v0 = v3(c[0], c[1], c[2]), v1 = v3(c[3], c[4], c[5]), v2 = v3(c[6], c[7], c[8]);
-                    const V3 m = 0.33333334f * (v0 + v1 + v2);
-                    const V3 d0 = v0 - m, d1 = v1 - m, d2 = v2 - m;
-                    keep = beam_keeps_ball(b, m, sqrtf(fmaxf(dot(d0, d0), fmaxf(dot(d1, d1), dot(d2, d2)))) * 1.0001f);
-                }
-            }
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, keep);
-        if (keep) list[n + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)(ob.n_cyl + i);
-        n += __popc(mask);
-    }
+    n_cyl_out = ncyl;
     __syncwarp();
     return n;
+}
+
+// ---------------------------------------------------------------- level-1 culling: facet x all sources
+// One warp per facet: bounding cone of the directions towards all sources, then one pass over the
+// primitives.  Writes ids[f*stride ..] and count[f] = (n_cyl_kept, n_total_kept) or (-1,-1).
+template <int SRC>
+__global__ void __launch_bounds__(256) facet_cull_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources,
+                                                         int S, unsigned short* __restrict__ ids, int2* __restrict__ count, int stride) {
+    extern __shared__ __align__(16) float smem[];
+    ObsSmem ob;
+    stage_obstructions(sc, smem, ob, true);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int n_obs = ob.n_cyl + ob.n_rest;
+    for (int f = blockIdx.x * nwarps + warp; f < sc.F; f += gridDim.x * nwarps) {
+        const float4 bnd = __ldg(sc.bounds + f);
+        const V3 c = v3(bnd.x, bnd.y, bnd.z);
+        // pass 1: mean unit direction, largest 1/D, degeneracy flag
+        V3 sum = v3(0.f, 0.f, 0.f);
+        float invDmax = 0.f;
+        bool bad = false;
+        for (int s = lane; s < S; s += 32) {
+            const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
+            const Beam b = make_beam<SRC>(bnd, src);
+            bad = bad || !b.ok;
+            sum = sum + b.u;
+            invDmax = fmaxf(invDmax, b.invD);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
+            invDmax = fmaxf(invDmax, __shfl_xor_sync(0xffffffffu, invDmax, o));
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        const float n2 = dot(sum, sum);
+        bad = bad || !(n2 > 1e-12f);
+        Beam fb;
+        fb.c = c; fb.R = bnd.w; fb.invD = invDmax; fb.u = rsqrtf(bad ? 1.f : n2) * sum;
+        // pass 2: largest chord between any source direction and the mean direction
+        float dmax2 = 0.f;
+        if (!bad) {
+            for (int s = lane; s < S; s += 32) {
+                const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
+                const Beam b = make_beam<SRC>(bnd, src);
+                const V3 dd = b.u - fb.u;
+                dmax2 = fmaxf(dmax2, dot(dd, dd));
+            }
+            for (int o = 16; o > 0; o >>= 1) dmax2 = fmaxf(dmax2, __shfl_xor_sync(0xffffffffu, dmax2, o));
+        }
+        fb.spread = sqrtf(dmax2) * 1.001f + 1e-6f;
+        fb.ok = !bad && fb.spread < 0.15f;
+        if (!fb.ok) { if (lane == 0) count[f] = make_int2(-1, -1); continue; }
+        int ncyl = 0;
+        const int n = build_list(ob, fb, (const unsigned short*)nullptr, ob.n_cyl, n_obs, ids + (size_t)f * stride, ncyl);
+        if (lane == 0) count[f] = make_int2(ncyl, n);
+    }
 }
 
 // ---------------------------------------------------------------- binning
@@ -122,10 +170,10 @@ __device__ __forceinline__ int build_list(const ObsSmem& ob, const Beam& b, unsi
 template <typename LUT>
 __device__ __forceinline__ void splat_soft_hex(const SensDev& se, const LUT* lut, float x, float y, float val, float* hist) {
     float xg, yg; hex_grid_coords(se, x, y, xg, yg);
-    const float q = (0.5773502691896257f * xg - yg / 3.0f) / se.size, r = (2.0f * yg / 3.0f) / se.size;
+    const float q = se.ax_qx * xg - se.ax_qy * yg, r = se.ax_ry * yg;
     float qb, rb; hex_round(q, r, qb, rb);
     if (!(fabsf(qb) < 1e6f && fabsf(rb) < 1e6f)) return;
-    const float ddx = xg - se.size_sqrt3 * (qb + rb / 2.0f), ddy = yg - se.size_1p5 * rb;
+    const float ddx = xg - se.size_sqrt3 * (qb + rb * 0.5f), ddy = yg - se.size_1p5 * rb;
     const int K = se.ksize;
     const float inv_sigma = 1.0f / se.sigma;
     float wsum = 0.f;
@@ -133,9 +181,9 @@ __device__ __forceinline__ void splat_soft_hex(const SensDev& se, const LUT* lut
         for (int oq = -K; oq <= K; ++oq)
             for (int orr = -K; orr <= K; ++orr) {
                 if (max(max(abs(oq), abs(orr)), abs(oq + orr)) > K) continue;
-                const float ox = se.size_sqrt3 * ((float)oq + (float)orr / 2.0f), oy = se.size_1p5 * (float)orr;
+                const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
                 const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
-                const float hd = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) / se.inradius;
+                const float hd = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) * se.inv_inradius;
                 const float z = hd * inv_sigma;
                 const float w = expf(-0.5f * z * z);
                 if (pass == 0) { wsum += w; continue; }
@@ -147,7 +195,7 @@ __device__ __forceinline__ void splat_soft_hex(const SensDev& se, const LUT* lut
 
 // DifferentiableSquareSensor.accumulate (square.py:144-172)
 __device__ __forceinline__ void splat_soft_square(const SensDev& se, float x, float y, float val, float* img) {
-    const float xp = (x - se.x0) / se.dx, yp = (y - se.y0) / se.dy;
+    const float xp = (x - se.x0) * se.inv_dx, yp = (y - se.y0) * se.inv_dy;
     const float xb = floorf(xp), yb = floorf(yp);
     const int K = se.ksize;
     if (!(xb >= (float)(-K - 1) && xb <= (float)(se.W + K) && yb >= (float)(-K - 1) && yb <= (float)(se.H + K))) return;
@@ -165,16 +213,43 @@ __device__ __forceinline__ void splat_soft_square(const SensDev& se, float x, fl
             }
 }
 
+// Warp-aggregated histogram add: lanes holding the same pixel are summed with shuffles and one lane
+// issues the shared-memory atomic (the PSF of one (facet, source) pair covers 1-3 hex pixels, so a
+// plain per-lane atomicAdd would serialise 32 ways on the CAS loop).  pix < 0 = nothing to add.
+// Must be called by all 32 lanes.
+__device__ __forceinline__ void warp_hist_add(float* hist, int pix, float val) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned todo = __ballot_sync(0xffffffffu, pix >= 0);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const int lp = __shfl_sync(0xffffffffu, pix, leader);
+        const bool mine = pix == lp;
+        float v = mine ? val : 0.f;
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (lane == (unsigned)leader) atomicAdd(hist + lp, v);
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+
 // ---------------------------------------------------------------- the kernel
+#ifndef IACT_MIN_BLOCKS
+#define IACT_MIN_BLOCKS 3
+#endif
 template <int SRC, int SENS, int MODE, bool STAGES>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, STAGES ? 1 : IACT_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
-             const LaunchPlan plan, float* __restrict__ out, float* __restrict__ out_val, int* __restrict__ out_pix) {
+             const LaunchPlan plan, const FacetLists fl, float* __restrict__ out, float* __restrict__ out_val,
+             int* __restrict__ out_pix) {
     extern __shared__ __align__(16) float smem[];
     ObsSmem ob;
-    stage_obstructions(sc, smem, ob);
-    const int n_obs = sc.n_cyl + sc.n_box + sc.n_sph + sc.n_obox + sc.n_tri;
-    float* p = smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri);
+    const bool cull = sc.cull != 0;
+    stage_obstructions(sc, smem, ob, cull);
+    const int n_obs = ob.n_cyl + ob.n_rest;
+    float* p = smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri, cull);
     float* hist = nullptr;
     const short* lut = nullptr;
     if (SENS == SENS_HEX) {
@@ -186,7 +261,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
         if (hist) for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) hist[i] = 0.f;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    unsigned short* list = sc.cull ? reinterpret_cast<unsigned short*>(p) + (size_t)warp * ((n_obs + 1) & ~1) : nullptr;
+    unsigned short* list = cull ? reinterpret_cast<unsigned short*>(p) + (size_t)warp * ((n_obs + 1) & ~1) : nullptr;
     __syncthreads();
 
     const int M = sc.M;
@@ -206,21 +281,26 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             const int f = f0 + fi;
             const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
             int n_list = 0, n_list_cyl = 0;
-            if (list) {
+            if (cull) {
                 const Beam beam = make_beam<SRC>(__ldg(sc.bounds + f), src);
-                n_list = build_list(ob, beam, list, n_list_cyl);
+                const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
+                if (cnt.x >= 0) n_list = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, n_list_cyl);
+                else            n_list = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, n_list_cyl);
             }
             const float4* tab = sc.world + ((size_t)f * M) * 2;
-            for (int m = m0 + lane; m < m1; m += 32) {
-                const float4 a = __ldg(tab + 2 * m), b = __ldg(tab + 2 * m + 1);
+            for (int mb = m0; mb < m1; mb += 32) {
+                const int m = mb + lane;
+                const bool live = m < m1;
+                const int mm = live ? m : m1 - 1;
+                const float4 a = __ldg(tab + 2 * mm), b = __ldg(tab + 2 * mm + 1);
                 V3 o = v3(a.x, a.y, a.z);
                 const V3 n = v3(b.x, b.y, b.z);
                 // render.py:129-133
                 V3 d;
                 if (SRC == IACT_SOURCE_POINT) {
                     d = o - src;
-                    const float nrm = sqrtf(dot(d, d));
-                    d = v3(d.x / nrm, d.y / nrm, d.z / nrm);
+                    const float inv = 1.0f / sqrtf(dot(d, d));
+                    d = inv * d;
                 } else {
                     d = src;
                 }
@@ -237,18 +317,21 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 float x, y;
                 plane_hit(sc.sens, o, d, x, y);
                 if (MODE == MODE_DEBUG) {
-                    const size_t ri = ((size_t)f * plan.S + s) * M + m;
-                    out[2 * ri] = x; out[2 * ri + 1] = y; out_val[ri] = val;
-                    if (out_pix) {
-                        int pix = -1;
-                        if (!soft) pix = SENS == SENS_HEX ? hex_pixel(sc.sens, lut, x, y) : square_pixel(sc.sens, x, y);
-                        out_pix[ri] = pix;
+                    if (live) {
+                        const size_t ri = ((size_t)f * plan.S + s) * M + m;
+                        out[2 * ri] = x; out[2 * ri + 1] = y; out_val[ri] = val;
+                        if (out_pix) {
+                            int pix = -1;
+                            if (!soft) pix = SENS == SENS_HEX ? hex_pixel(sc.sens, lut, x, y) : square_pixel(sc.sens, x, y);
+                            out_pix[ri] = pix;
+                        }
                     }
-                } else if (val != 0.f) {
+                } else {
+                    const bool add = live && val != 0.f;
                     if (SENS == SENS_HEX) {
-                        if (soft) splat_soft_hex(sc.sens, lut, x, y, val, hist);
-                        else { const int pix = hex_pixel(sc.sens, lut, x, y); if (pix >= 0) atomicAdd(hist + pix, val); }
-                    } else {
+                        if (soft) { if (add) splat_soft_hex(sc.sens, lut, x, y, val, hist); }
+                        else warp_hist_add(hist, add ? hex_pixel(sc.sens, lut, x, y) : -1, val);
+                    } else if (add) {
                         if (soft) splat_soft_square(sc.sens, x, y, val, gout);
                         else { const int pix = square_pixel(sc.sens, x, y); if (pix >= 0) atomicAdd(gout + pix, val); }
                     }
@@ -278,29 +361,32 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     }
 }
 
-// Culling statistics: candidate-list lengths summed over all (facet, source) pairs.
+// Culling statistics: level-2 candidate-list lengths summed over all (facet, source) pairs.
 template <int SRC>
 __global__ void __launch_bounds__(256) cull_stats_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources,
-                                                         int S, unsigned long long* __restrict__ out) {
+                                                         int S, const FacetLists fl, unsigned long long* __restrict__ out) {
     extern __shared__ __align__(16) float smem[];
     ObsSmem ob;
-    stage_obstructions(sc, smem, ob);
-    const int n_obs = sc.n_cyl + sc.n_box + sc.n_sph + sc.n_obox + sc.n_tri;
+    stage_obstructions(sc, smem, ob, true);
+    const int n_obs = ob.n_cyl + ob.n_rest;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    unsigned short* list = reinterpret_cast<unsigned short*>(smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri))
+    unsigned short* list = reinterpret_cast<unsigned short*>(smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri, true))
                            + (size_t)warp * ((n_obs + 1) & ~1);
     __syncthreads();
-    unsigned long long a = 0, b = 0, c = 0;
+    unsigned long long a = 0, b = 0, c = 0, l1 = 0;
     const long long n_pairs = (long long)sc.F * S;
     for (long long i = (long long)blockIdx.x * nwarps + warp; i < n_pairs; i += (long long)gridDim.x * nwarps) {
         const int f = (int)(i / S), s = (int)(i - (long long)f * S);
         const V3 src = v3(sources[3 * s], sources[3 * s + 1], sources[3 * s + 2]);
-        int ncyl = 0;
-        const int n = build_list(ob, make_beam<SRC>(__ldg(sc.bounds + f), src), list, ncyl);
-        a += ncyl; b += n - ncyl; c += 1;
+        const Beam beam = make_beam<SRC>(__ldg(sc.bounds + f), src);
+        const int2 cnt = __ldg(fl.count + f);
+        int ncyl = 0, n;
+        if (cnt.x >= 0) n = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, ncyl);
+        else            n = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, ncyl);
+        a += ncyl; b += n - ncyl; c += 1; l1 += cnt.x >= 0 ? cnt.y : n_obs;
         __syncwarp();
     }
-    if (lane == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); atomicAdd(out + 2, c); }
+    if (lane == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); atomicAdd(out + 2, c); atomicAdd(out + 3, l1); }
 }
 
 // sensor.accumulate on free-standing hits: one thread per hit, red.global into the image.
@@ -343,12 +429,18 @@ void fill_sensor(const IactSensor& s, SensDev& d) {
     d.ndotp = d.nrm[0] * d.pos[0] + d.nrm[1] * d.pos[1] + d.nrm[2] * d.pos[2];
     d.W = s.width; d.H = s.height;
     d.x0 = (float)s.x0; d.y0 = (float)s.y0; d.dx = (float)s.dx; d.dy = (float)s.dy; d.edge = (float)s.edge_width;
+    d.inv_dx = s.dx != 0.0 ? (float)(1.0 / s.dx) : 0.f; d.inv_dy = s.dy != 0.0 ? (float)(1.0 / s.dy) : 0.f;
     d.goffx = (float)s.grid_offset[0]; d.goffy = (float)s.grid_offset[1];
     const float ang = (float)(-s.grid_rotation);
     d.cr = cosf(ang); d.sr = sinf(ang);
     d.size = (float)s.hex_size; d.size_sqrt3 = (float)(s.hex_size * 1.7320508075688772);
     d.size_1p5 = (float)(s.hex_size * 1.5); d.inradius = (float)s.hex_inradius;
     d.edge_thr = s.hex_inradius != 0.0 ? (float)(1.0 - s.edge_width / s.hex_inradius) : 1.0f;
+    if (s.hex_size != 0.0) {
+        d.ax_qx = (float)(0.5773502691896257 / s.hex_size); d.ax_qy = (float)(1.0 / (3.0 * s.hex_size));
+        d.ax_ry = (float)(2.0 / (3.0 * s.hex_size));
+    }
+    d.inv_inradius = s.hex_inradius != 0.0 ? (float)(1.0 / s.hex_inradius) : 0.f;
     d.qmin = s.q_min; d.rmin = s.r_min; d.tq = s.table_q; d.tr = s.table_r; d.npix = s.n_pixels;
     d.lookup = s.lookup; d.sigma = (float)s.sigma; d.ksize = s.kernel_size;
 }
@@ -388,13 +480,13 @@ int fill_scene(const IactScene* s, SceneDev& d) {
     }
     if (se.kind >= IACT_SENSOR_SOFT_SQUARE) IACT_REQUIRE(se.sigma > 0.0 && se.kernel_size >= 0 && se.kernel_size <= 8, "bad soft-sensor parameters");
     fill_sensor(se, d.sens);
-    d.cull = s->cull;
+    d.cull = s->cull && (d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri) > 0;
     return IACT_OK;
 }
 
 size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
     const int n_obs = d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri;
-    size_t fl = obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri);
+    size_t fl = obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, d.cull != 0);
     if (sens == SENS_HEX) {
         if (mode != MODE_DEBUG) fl += d.sens.npix;
         fl += (d.sens.tq * d.sens.tr + 1) / 2;
@@ -404,8 +496,40 @@ size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
     return bytes + 16;
 }
 
+// Scratch for the level-1 lists, stream-ordered (no synchronisation).
+struct Scratch {
+    void* ptr = nullptr; cudaStream_t st = nullptr;
+    int alloc(size_t bytes, cudaStream_t s) { st = s; return iact_check_cuda(cudaMallocAsync(&ptr, bytes, s), "cudaMallocAsync"); }
+    ~Scratch() { if (ptr) cudaFreeAsync(ptr, st); }
+};
+
+// Launch level-1 culling into `scr`; fills `fl`.
+int run_facet_cull(const SceneDev& d, const float* sources, int S, int source_type, Scratch& scr, FacetLists& fl, cudaStream_t st) {
+    fl.ids = nullptr; fl.count = nullptr; fl.stride = 0;
+    if (!d.cull) return IACT_OK;
+    const int n_obs = d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri;
+    const int stride = (n_obs + 7) & ~7;
+    const size_t count_bytes = ((size_t)d.F * sizeof(int2) + 15) & ~(size_t)15;
+    int rc = scr.alloc(count_bytes + (size_t)d.F * stride * sizeof(unsigned short), st);
+    if (rc) return rc;
+    int2* count = reinterpret_cast<int2*>(scr.ptr);
+    unsigned short* ids = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(scr.ptr) + count_bytes);
+    const size_t smem = (size_t)obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, true) * 4 + 16;
+    if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
+    const int blocks = std::max(1, std::min((d.F + 7) / 8, sm_count() * 2));
+    auto launch = [&](auto kern) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<blocks, 256, smem, st>>>(d, sources, S, ids, count, stride);
+    };
+    if (source_type == IACT_SOURCE_POINT) launch(facet_cull_kernel<IACT_SOURCE_POINT>);
+    else launch(facet_cull_kernel<IACT_SOURCE_PARALLEL>);
+    iact_count_launch();
+    fl.ids = ids; fl.count = count; fl.stride = stride;
+    return iact_check_cuda(cudaGetLastError(), "facet_cull_kernel launch");
+}
+
 template <int SRC, int SENS, int MODE, bool STAGES>
-int launch_variant(const SceneDev& d, const float* sources, const float* values, const LaunchPlan& plan,
+int launch_variant(const SceneDev& d, const float* sources, const float* values, const LaunchPlan& plan, const FacetLists& fl,
                    float* out, float* out_val, int* out_pix, cudaStream_t stream) {
     const int threads = 256;
     const size_t smem = smem_bytes(d, SENS, MODE, threads / 32);
@@ -417,27 +541,28 @@ int launch_variant(const SceneDev& d, const float* sources, const float* values,
     if (occ < 1) occ = 1;
     const long long max_blocks = (long long)sm_count() * occ;
     const unsigned grid = (unsigned)std::max(1LL, std::min(plan.n_items, max_blocks));
-    kern<<<grid, threads, smem, stream>>>(d, sources, values, plan, out, out_val, out_pix);
+    kern<<<grid, threads, smem, stream>>>(d, sources, values, plan, fl, out, out_val, out_pix);
     iact_count_launch();
     return iact_check_cuda(cudaGetLastError(), "trace_kernel launch");
 }
 
+#define ARGS const SceneDev& d, const float* a, const float* b, const LaunchPlan& p, const FacetLists& fl, float* o, float* ov, int* op, cudaStream_t st
+#define PASS d, a, b, p, fl, o, ov, op, st
 template <int SRC, int SENS, int MODE>
-int launch_stages(const SceneDev& d, const float* a, const float* b, const LaunchPlan& p, float* o, float* ov, int* op, cudaStream_t st) {
-    return d.n_stages > 0 ? launch_variant<SRC, SENS, MODE, true>(d, a, b, p, o, ov, op, st)
-                          : launch_variant<SRC, SENS, MODE, false>(d, a, b, p, o, ov, op, st);
+int launch_stages(ARGS) {
+    return d.n_stages > 0 ? launch_variant<SRC, SENS, MODE, true>(PASS) : launch_variant<SRC, SENS, MODE, false>(PASS);
 }
 template <int SRC, int MODE>
-int launch_sens(const SceneDev& d, const float* a, const float* b, const LaunchPlan& p, float* o, float* ov, int* op, cudaStream_t st) {
+int launch_sens(ARGS) {
     const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
-    return hex ? launch_stages<SRC, SENS_HEX, MODE>(d, a, b, p, o, ov, op, st)
-               : launch_stages<SRC, SENS_SQUARE, MODE>(d, a, b, p, o, ov, op, st);
+    return hex ? launch_stages<SRC, SENS_HEX, MODE>(PASS) : launch_stages<SRC, SENS_SQUARE, MODE>(PASS);
 }
 template <int MODE>
-int launch_src(int source_type, const SceneDev& d, const float* a, const float* b, const LaunchPlan& p, float* o, float* ov, int* op, cudaStream_t st) {
-    return source_type == IACT_SOURCE_POINT ? launch_sens<IACT_SOURCE_POINT, MODE>(d, a, b, p, o, ov, op, st)
-                                            : launch_sens<IACT_SOURCE_PARALLEL, MODE>(d, a, b, p, o, ov, op, st);
+int launch_src(int source_type, ARGS) {
+    return source_type == IACT_SOURCE_POINT ? launch_sens<IACT_SOURCE_POINT, MODE>(PASS) : launch_sens<IACT_SOURCE_PARALLEL, MODE>(PASS);
 }
+#undef ARGS
+#undef PASS
 
 // Split S x F x M rays into block items (source, facet chunk) and warp items (facet, sample range).
 LaunchPlan make_plan(const SceneDev& d, int S, int mode) {
@@ -484,30 +609,41 @@ int run(const IactScene* scene, const float* sources, const float* values, int S
     if (empty) return IACT_OK;
     plan.S = S;
     plan.n_items = (long long)S * plan.n_chunks;
+    Scratch scr;
+    FacetLists fl;
+    fl.ids = nullptr; fl.count = nullptr; fl.stride = 0;
+    // level-1 lists pay off once a facet is seen from several sources
+    if (d.cull && S >= 4) { rc = run_facet_cull(d, sources, S, source_type, scr, fl, st); if (rc) return rc; }
     switch (mode) {
-        case MODE_RENDER: return launch_src<MODE_RENDER>(source_type, d, sources, values, plan, out, out_val, out_pix, st);
-        case MODE_MATRIX: return launch_src<MODE_MATRIX>(source_type, d, sources, values, plan, out, out_val, out_pix, st);
-        default:          return launch_src<MODE_DEBUG>(source_type, d, sources, values, plan, out, out_val, out_pix, st);
+        case MODE_RENDER: return launch_src<MODE_RENDER>(source_type, d, sources, values, plan, fl, out, out_val, out_pix, st);
+        case MODE_MATRIX: return launch_src<MODE_MATRIX>(source_type, d, sources, values, plan, fl, out, out_val, out_pix, st);
+        default:          return launch_src<MODE_DEBUG>(source_type, d, sources, values, plan, fl, out, out_val, out_pix, st);
     }
 }
 
 }  // namespace
 
 extern "C" int iact_cull_stats(const IactScene* scene, const float* sources, int n_sources, int source_type,
-                               unsigned long long* out3, void* stream) {
+                               unsigned long long* out4, void* stream) {
     SceneDev d;
+    IACT_REQUIRE(scene, "null scene");
     IactScene tmp = *scene;
     tmp.cull = 1;
     int rc = fill_scene(&tmp, d);
     if (rc) return rc;
-    IACT_REQUIRE(sources && out3 && n_sources > 0 && d.F > 0, "bad arguments");
+    IACT_REQUIRE(sources && out4 && n_sources > 0 && d.F > 0, "bad arguments");
+    IACT_REQUIRE(d.cull, "scene has no obstructions");
     cudaStream_t st = (cudaStream_t)stream;
-    IACT_CUDA(cudaMemsetAsync(out3, 0, 3 * sizeof(unsigned long long), st));
+    IACT_CUDA(cudaMemsetAsync(out4, 0, 4 * sizeof(unsigned long long), st));
+    Scratch scr;
+    FacetLists fl;
+    rc = run_facet_cull(d, sources, n_sources, source_type, scr, fl, st);
+    if (rc) return rc;
     const size_t smem = smem_bytes(d, SENS_SQUARE, MODE_DEBUG, 8);
     if (smem > 200 * 1024) { iact_set_error("scene too large for shared memory"); return IACT_ERR_UNSUPPORTED; }
     auto launch = [&](auto kern) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<sm_count() * 4, 256, smem, st>>>(d, sources, n_sources, out3);
+        kern<<<sm_count() * 4, 256, smem, st>>>(d, sources, n_sources, fl, out4);
     };
     if (source_type == IACT_SOURCE_POINT) launch(cull_stats_kernel<IACT_SOURCE_POINT>);
     else launch(cull_stats_kernel<IACT_SOURCE_PARALLEL>);

@@ -192,10 +192,10 @@ int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
                     const float* cotangent, const IactGrads* grads, void* stream);
 
 /* Diagnostics for the roofline: candidate-list lengths of the conservative obstruction culling,
- * summed over all (facet, source) pairs.  out3: device uint64[3] = {sum cylinders kept,
- * sum other primitives kept, number of pairs}. */
+ * summed over all (facet, source) pairs.  out4: device uint64[4] = {sum cylinders kept,
+ * sum other primitives kept, number of pairs, sum of the facet-level (level-1) list lengths}. */
 int iact_cull_stats(const IactScene* scene, const float* sources, int n_sources, int source_type,
-                    unsigned long long* out3, void* stream);
+                    unsigned long long* out4, void* stream);
 
 /* Roofline probes (bench.py): dependent-free FP32 FMA throughput in FLOP/s written to
  * *out_flops, shared-memory float atomicAdd throughput in atomics/s to *out_atomics. */
