@@ -499,7 +499,22 @@ size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
 // Scratch for the level-1 lists, stream-ordered (no synchronisation).
 struct Scratch {
     void* ptr = nullptr; cudaStream_t st = nullptr;
-    int alloc(size_t bytes, cudaStream_t s) { st = s; return iact_check_cuda(cudaMallocAsync(&ptr, bytes, s), "cudaMallocAsync"); }
+    int alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        // keep freed scratch in the device's default pool across synchronisations (the default
+        // release threshold of 0 hands it back to the OS at every sync and re-maps it on the next call)
+        static thread_local int pooled_dev = -1;
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev != pooled_dev) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pooled_dev = dev;
+        }
+        return iact_check_cuda(cudaMallocAsync(&ptr, bytes, s), "cudaMallocAsync");
+    }
     ~Scratch() { if (ptr) cudaFreeAsync(ptr, st); }
 };
 
@@ -592,6 +607,7 @@ int run(const IactScene* scene, const float* sources, const float* values, int S
     if (rc) return rc;
     IACT_REQUIRE(S >= 0, "negative source count");
     IACT_REQUIRE(source_type == IACT_SOURCE_POINT || source_type == IACT_SOURCE_PARALLEL, "bad source_type");
+    if (mode != MODE_RENDER && S == 0) return IACT_OK;                      // zero-row outputs have no storage
     IACT_REQUIRE(out, "null output");
     cudaStream_t st = (cudaStream_t)stream;
     const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;

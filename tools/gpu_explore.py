@@ -51,6 +51,23 @@ def main():
                 med, mn = timeit(lambda: render(tel, src, val, "point", sensor), n=3 if not cull else 5, warm=1)
                 print(f"CT5 render S=4096 M={M} sensor={sensor} cull={cull}: {med:.2f} ms  -> {rays/med/1e6:.1f} Grays/s")
         Rm.cull_obstructions = True
+    # host-side cost of one render call (ctypes + scene packing + launches), and back-to-back device time
+    tel = build_telescope(ct5, I.MCIntegrator(115), I.random.key(0))
+    src = torch.from_numpy(point_grid(64, 1.5)).cuda(); val = torch.ones(len(src), device="cuda")
+    render(tel, src, val, "point", 0); torch.cuda.synchronize()
+    host = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        t = time.perf_counter(); render(tel, src, val, "point", 0); host.append(time.perf_counter() - t)
+    e1.record(); torch.cuda.synchronize()
+    print(f"20 back-to-back renders: {e0.elapsed_time(e1)/20:.2f} ms/call device; host call median {np.median(host)*1e6:.0f} us max {np.max(host)*1e6:.0f} us")
+    host = []
+    for _ in range(10):
+        torch.cuda.synchronize()
+        t = time.perf_counter(); render(tel, src, val, "point", 0); host.append(time.perf_counter() - t)
+    torch.cuda.synchronize()
+    print(f"render after sync: host call median {np.median(host)*1e6:.0f} us max {np.max(host)*1e6:.0f} us")
     ct3 = load_packed_config("CT3")
     for M in (64, 1000):
         tel = build_telescope(ct3, I.MCIntegrator(M), I.random.key(42)).apply_roughness(24)
