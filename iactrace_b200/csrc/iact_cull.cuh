@@ -1,0 +1,317 @@
+// Shared between the forward (iact_render.cu) and backward (iact_vjp.cu) kernels: work plan,
+// conservative hierarchical obstruction culling, scene packing on the host.
+#pragma once
+#include "iact_trace.cuh"
+#include <algorithm>
+#include <cstring>
+
+namespace {
+
+enum { MODE_RENDER = 0, MODE_MATRIX = 1, MODE_DEBUG = 2 };
+enum { SENS_SQUARE = 0, SENS_HEX = 1 };
+
+struct LaunchPlan {
+    int S, n_chunks, chunk_facets, msplit, msize;
+    long long n_items;
+};
+
+// Level-1 culling output: per facet a list of primitive ids (cylinders first) and its two counts;
+// count.x < 0 means "no facet-level culling for this facet" (degenerate beam): use every primitive.
+struct FacetLists { const unsigned short* ids; const int2* count; int stride; };
+
+struct Beam { V3 c, u; float R, invD, spread; bool ok; };
+
+// Beam of all rays from the facet's bounding sphere towards one source (and beyond: the reference's
+// shadow ray is infinite, render.py:138 + :40).
+template <int SRC>
+__device__ __forceinline__ Beam make_beam(float4 bnd, V3 src) {
+    Beam b;
+    b.c = v3(bnd.x, bnd.y, bnd.z); b.R = bnd.w; b.spread = 0.f;
+    V3 a = SRC == IACT_SOURCE_POINT ? src - b.c : -src;
+    const float n2 = dot(a, a);
+    b.ok = n2 > 1e-30f && n2 < 1e37f;
+    const float inv = rsqrtf(b.ok ? n2 : 1.f);
+    b.u = inv * a;
+    b.invD = SRC == IACT_SOURCE_POINT ? inv : 0.f;
+    if (b.R * b.invD > 0.1f) b.ok = false;              // source inside/near the facet: no culling
+    return b;
+}
+
+// Conservative: false only if no ray of the beam can come within r of the segment [p1,p2].
+// A ray starts within R of c and its direction is within `spread` (chord) + 1.5708 R/D (point-source
+// parallax) of u; rays are half-lines, so everything behind the facet is out of reach.
+__device__ __forceinline__ bool beam_keeps_capsule(const Beam& b, V3 p1, V3 p2, float r) {
+    const V3 a1 = p1 - b.c, a2 = p2 - b.c;
+    const float t1 = dot(a1, b.u), t2 = dot(a2, b.u);
+    const float tmx = fmaxf(t1, t2);
+    const float marg = 2e-3f;
+    if (tmx + r < -(b.R + marg)) return false;          // wholly behind every ray origin
+    const float tmax = 1.1f * (fmaxf(tmx, 0.f) + r + b.R);       // 1/cos(max beam half-angle 0.31 rad) < 1.1
+    const float Reff = b.R * (1.0f + 1.5708f * tmax * b.invD) + b.spread * tmax + marg + 1e-5f * tmax;
+    const V3 q1 = a1 - t1 * b.u, q2 = a2 - t2 * b.u;
+    const V3 e = q2 - q1;
+    const float ee = dot(e, e);
+    const float s = ee > 1e-20f ? fminf(fmaxf(-dot(q1, e) * frcp_fast(ee), 0.f), 1.f) : 0.f;
+    const V3 dv = q1 + s * e;
+    const float lim = Reff + r;
+    return dot(dv, dv) <= lim * lim;
+}
+
+__device__ __forceinline__ bool keep_primitive(const ObsSmem& ob, const Beam& b, int id) {
+    if (id < ob.n_cyl) {
+        const float* c = ob.ccyl; const int n = ob.n_cyl;
+        return beam_keeps_capsule(b, v3(c[id], c[n + id], c[2 * n + id]), v3(c[3 * n + id], c[4 * n + id], c[5 * n + id]), c[6 * n + id]);
+    }
+    id -= ob.n_cyl;
+    const float* c = ob.cball; const int n = ob.n_rest;
+    const V3 m = v3(c[id], c[n + id], c[2 * n + id]);
+    return beam_keeps_capsule(b, m, m, c[3 * n + id]);
+}
+
+// Warp-cooperative compaction of the primitives a beam can reach.  `cand` (may be null = all
+// primitives) lists candidate ids, cylinders first (n_cand_cyl of n_cand).  Writes ids to `out`
+// (shared or global), returns the total and sets n_cyl_out.  Order is preserved.
+__device__ __forceinline__ int build_list(const ObsSmem& ob, const Beam& b, const unsigned short* cand, int n_cand_cyl,
+                                          int n_cand, unsigned short* out, int& n_cyl_out) {
+    const unsigned lane = threadIdx.x & 31u;
+    int n = 0, ncyl = 0;
+    for (int base = 0; base < n_cand; base += 32) {
+        const int i = base + (int)lane;
+        bool keep = false;
+        int id = 0;
+        if (i < n_cand) {
+            id = cand ? (int)cand[i] : i;
+            keep = !b.ok || keep_primitive(ob, b, id);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) out[n + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)id;
+        n += __popc(mask);
+        // cylinders come first in `cand`: count those kept among positions < n_cand_cyl
+        const int lim = n_cand_cyl - base;
+        ncyl += lim >= 32 ? __popc(mask) : (lim > 0 ? __popc(mask & ((1u << lim) - 1u)) : 0);
+    }
+    n_cyl_out = ncyl;
+    __syncwarp();
+    return n;
+}
+
+// ---------------------------------------------------------------- level-1 culling: facet x all sources
+// One warp per facet: bounding cone of the directions towards all sources, then one pass over the
+// primitives.  Writes ids[f*stride ..] and count[f] = (n_cyl_kept, n_total_kept) or (-1,-1).
+template <int SRC>
+__global__ void __launch_bounds__(256) facet_cull_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources,
+                                                         int S, unsigned short* __restrict__ ids, int2* __restrict__ count, int stride) {
+    extern __shared__ __align__(16) float smem[];
+    ObsSmem ob;
+    stage_obstructions(sc, smem, ob, true);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int n_obs = ob.n_cyl + ob.n_rest;
+    for (int f = blockIdx.x * nwarps + warp; f < sc.F; f += gridDim.x * nwarps) {
+        const float4 bnd = __ldg(sc.bounds + f);
+        const V3 c = v3(bnd.x, bnd.y, bnd.z);
+        // pass 1: mean unit direction, largest 1/D, degeneracy flag
+        V3 sum = v3(0.f, 0.f, 0.f);
+        float invDmax = 0.f;
+        bool bad = false;
+        for (int s = lane; s < S; s += 32) {
+            const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
+            const Beam b = make_beam<SRC>(bnd, src);
+            bad = bad || !b.ok;
+            sum = sum + b.u;
+            invDmax = fmaxf(invDmax, b.invD);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o);
+            sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o);
+            invDmax = fmaxf(invDmax, __shfl_xor_sync(0xffffffffu, invDmax, o));
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        const float n2 = dot(sum, sum);
+        bad = bad || !(n2 > 1e-12f);
+        Beam fb;
+        fb.c = c; fb.R = bnd.w; fb.invD = invDmax; fb.u = rsqrtf(bad ? 1.f : n2) * sum;
+        // pass 2: largest chord between any source direction and the mean direction
+        float dmax2 = 0.f;
+        if (!bad) {
+            for (int s = lane; s < S; s += 32) {
+                const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
+                const Beam b = make_beam<SRC>(bnd, src);
+                const V3 dd = b.u - fb.u;
+                dmax2 = fmaxf(dmax2, dot(dd, dd));
+            }
+            for (int o = 16; o > 0; o >>= 1) dmax2 = fmaxf(dmax2, __shfl_xor_sync(0xffffffffu, dmax2, o));
+        }
+        fb.spread = sqrtf(dmax2) * 1.001f + 1e-6f;
+        fb.ok = !bad && fb.spread < 0.15f;
+        if (!fb.ok) { if (lane == 0) count[f] = make_int2(-1, -1); continue; }
+        int ncyl = 0;
+        const int n = build_list(ob, fb, (const unsigned short*)nullptr, ob.n_cyl, n_obs, ids + (size_t)f * stride, ncyl);
+        if (lane == 0) count[f] = make_int2(ncyl, n);
+    }
+}
+
+// ---------------------------------------------------------------- host side
+static int g_sm_count = 0;
+
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+void fill_sensor(const IactSensor& s, SensDev& d) {
+    memset(&d, 0, sizeof(d));
+    d.kind = s.kind;
+    // euler_to_matrix (transforms.py:72-106) in float32
+    const float D2R = 0.017453292519943295f;
+    const float rx = s.euler[0] * D2R, ry = s.euler[1] * D2R, rz = s.euler[2] * D2R;
+    const float cx = cosf(rx), sx = sinf(rx), cy = cosf(ry), sy = sinf(ry), cz = cosf(rz), sz = sinf(rz);
+    const float a[3][3] = {{cy, sy * sx, sy * cx}, {0.f, cx, -sx}, {-sy, cy * sx, cy * cx}};
+    float R[3][3];
+    for (int j = 0; j < 3; ++j) { R[0][j] = cz * a[0][j] - sz * a[1][j]; R[1][j] = sz * a[0][j] + cz * a[1][j]; R[2][j] = a[2][j]; }
+    for (int i = 0; i < 3; ++i) { d.pos[i] = s.position[i]; d.u1[i] = R[i][0]; d.u2[i] = R[i][1]; d.nrm[i] = R[i][2]; }
+    d.ndotp = d.nrm[0] * d.pos[0] + d.nrm[1] * d.pos[1] + d.nrm[2] * d.pos[2];
+    d.W = s.width; d.H = s.height;
+    d.x0 = (float)s.x0; d.y0 = (float)s.y0; d.dx = (float)s.dx; d.dy = (float)s.dy; d.edge = (float)s.edge_width;
+    d.inv_dx = s.dx != 0.0 ? (float)(1.0 / s.dx) : 0.f; d.inv_dy = s.dy != 0.0 ? (float)(1.0 / s.dy) : 0.f;
+    d.goffx = (float)s.grid_offset[0]; d.goffy = (float)s.grid_offset[1];
+    const float ang = (float)(-s.grid_rotation);
+    d.cr = cosf(ang); d.sr = sinf(ang);
+    d.size = (float)s.hex_size; d.size_sqrt3 = (float)(s.hex_size * 1.7320508075688772);
+    d.size_1p5 = (float)(s.hex_size * 1.5); d.inradius = (float)s.hex_inradius;
+    d.edge_thr = s.hex_inradius != 0.0 ? (float)(1.0 - s.edge_width / s.hex_inradius) : 1.0f;
+    if (s.hex_size != 0.0) {
+        d.ax_qx = (float)(0.5773502691896257 / s.hex_size); d.ax_qy = (float)(1.0 / (3.0 * s.hex_size));
+        d.ax_ry = (float)(2.0 / (3.0 * s.hex_size));
+    }
+    d.inv_inradius = s.hex_inradius != 0.0 ? (float)(1.0 / s.hex_inradius) : 0.f;
+    d.qmin = s.q_min; d.rmin = s.r_min; d.tq = s.table_q; d.tr = s.table_r; d.npix = s.n_pixels;
+    d.lookup = s.lookup; d.sigma = (float)s.sigma; d.ksize = s.kernel_size;
+}
+
+int fill_scene(const IactScene* s, SceneDev& d) {
+    IACT_REQUIRE(s, "null scene");
+    IACT_REQUIRE(s->n_facets >= 0 && s->n_samples >= 0, "negative facet/sample count");
+    IACT_REQUIRE(s->n_facets == 0 || s->n_samples == 0 || (s->world && s->bounds), "null world table");
+    IACT_REQUIRE(s->n_stages >= 0 && s->n_stages <= IACT_MAX_STAGES, "too many optical stages");
+    IACT_REQUIRE(s->n_cyl >= 0 && s->n_box >= 0 && s->n_sph >= 0 && s->n_obox >= 0 && s->n_tri >= 0, "negative obstruction count");
+    IACT_REQUIRE((long long)s->n_cyl + s->n_box + s->n_sph + s->n_obox + s->n_tri < 65535, "too many obstructions (max 65534)");
+    memset(&d, 0, sizeof(d));
+    d.F = s->n_facets; d.M = s->n_samples;
+    d.world = reinterpret_cast<const float4*>(s->world); d.bounds = reinterpret_cast<const float4*>(s->bounds);
+    d.n_cyl = s->n_cyl; d.cyl_p1 = s->cyl_p1; d.cyl_p2 = s->cyl_p2; d.cyl_r = s->cyl_r;
+    d.n_box = s->n_box; d.box_p1 = s->box_p1; d.box_p2 = s->box_p2;
+    d.n_sph = s->n_sph; d.sph_c = s->sph_c; d.sph_r = s->sph_r;
+    d.n_obox = s->n_obox; d.obox_c = s->obox_c; d.obox_h = s->obox_h; d.obox_R = s->obox_R;
+    d.n_tri = s->n_tri; d.tri_v0 = s->tri_v0; d.tri_v1 = s->tri_v1; d.tri_v2 = s->tri_v2;
+    IACT_REQUIRE(!d.n_cyl || (d.cyl_p1 && d.cyl_p2 && d.cyl_r), "null cylinder table");
+    IACT_REQUIRE(!d.n_box || (d.box_p1 && d.box_p2), "null box table");
+    IACT_REQUIRE(!d.n_sph || (d.sph_c && d.sph_r), "null sphere table");
+    IACT_REQUIRE(!d.n_obox || (d.obox_c && d.obox_h && d.obox_R), "null oriented-box table");
+    IACT_REQUIRE(!d.n_tri || (d.tri_v0 && d.tri_v1 && d.tri_v2), "null triangle table");
+    d.n_stages = s->n_stages;
+    for (int i = 0; i < s->n_stages; ++i) {
+        d.stages[i].n = s->stages[i].n_mirrors; d.stages[i].rec = s->stages[i].records; d.stages[i].verts = s->stages[i].verts;
+        IACT_REQUIRE(d.stages[i].n >= 0 && (d.stages[i].n == 0 || d.stages[i].rec), "bad mirror stage");
+    }
+    const IactSensor& se = s->sensor;
+    IACT_REQUIRE(se.kind >= IACT_SENSOR_SQUARE && se.kind <= IACT_SENSOR_SOFT_HEX, "unknown sensor kind");
+    if (se.kind == IACT_SENSOR_SQUARE || se.kind == IACT_SENSOR_SOFT_SQUARE) {
+        IACT_REQUIRE(se.width > 0 && se.height > 0 && se.dx != 0.0 && se.dy != 0.0, "bad square sensor");
+    } else {
+        IACT_REQUIRE(se.n_pixels > 0 && se.n_pixels < 32768 && se.table_q > 0 && se.table_r > 0 && se.lookup && se.hex_size > 0.0,
+                     "bad hexagonal sensor (n_pixels must be < 32768)");
+    }
+    if (se.kind >= IACT_SENSOR_SOFT_SQUARE) IACT_REQUIRE(se.sigma > 0.0 && se.kernel_size >= 0 && se.kernel_size <= 8, "bad soft-sensor parameters");
+    fill_sensor(se, d.sens);
+    d.cull = s->cull && (d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri) > 0;
+    return IACT_OK;
+}
+
+size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
+    const int n_obs = d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri;
+    size_t fl = obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, d.cull != 0);
+    if (sens == SENS_HEX) {
+        if (mode != MODE_DEBUG) fl += d.sens.npix;
+        fl += (d.sens.tq * d.sens.tr + 1) / 2;
+    }
+    size_t bytes = fl * 4;
+    if (d.cull) bytes += (size_t)nwarps * ((n_obs + 1) & ~1) * 2;
+    return bytes + 16;
+}
+
+// Scratch for the level-1 lists, stream-ordered (no synchronisation).
+struct Scratch {
+    void* ptr = nullptr; cudaStream_t st = nullptr;
+    int alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        // keep freed scratch in the device's default pool across synchronisations (the default
+        // release threshold of 0 hands it back to the OS at every sync and re-maps it on the next call)
+        static thread_local int pooled_dev = -1;
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && dev != pooled_dev) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pooled_dev = dev;
+        }
+        return iact_check_cuda(cudaMallocAsync(&ptr, bytes, s), "cudaMallocAsync");
+    }
+    ~Scratch() { if (ptr) cudaFreeAsync(ptr, st); }
+};
+
+// Launch level-1 culling into `scr`; fills `fl`.
+int run_facet_cull(const SceneDev& d, const float* sources, int S, int source_type, Scratch& scr, FacetLists& fl, cudaStream_t st) {
+    fl.ids = nullptr; fl.count = nullptr; fl.stride = 0;
+    if (!d.cull) return IACT_OK;
+    const int n_obs = d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri;
+    const int stride = (n_obs + 7) & ~7;
+    const size_t count_bytes = ((size_t)d.F * sizeof(int2) + 15) & ~(size_t)15;
+    int rc = scr.alloc(count_bytes + (size_t)d.F * stride * sizeof(unsigned short), st);
+    if (rc) return rc;
+    int2* count = reinterpret_cast<int2*>(scr.ptr);
+    unsigned short* ids = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(scr.ptr) + count_bytes);
+    const size_t smem = (size_t)obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, true) * 4 + 16;
+    if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
+    const int blocks = std::max(1, std::min((d.F + 7) / 8, sm_count() * 2));
+    auto launch = [&](auto kern) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<blocks, 256, smem, st>>>(d, sources, S, ids, count, stride);
+    };
+    if (source_type == IACT_SOURCE_POINT) launch(facet_cull_kernel<IACT_SOURCE_POINT>);
+    else launch(facet_cull_kernel<IACT_SOURCE_PARALLEL>);
+    iact_count_launch();
+    fl.ids = ids; fl.count = count; fl.stride = stride;
+    return iact_check_cuda(cudaGetLastError(), "facet_cull_kernel launch");
+}
+
+// Split S x F x M rays into block items (source, facet chunk) and warp items (facet, sample range).
+LaunchPlan make_plan(const SceneDev& d, int S, int mode) {
+    LaunchPlan p;
+    p.S = S;
+    const long long target = (long long)sm_count() * 16;          // block items wanted for balance
+    int n_chunks = 1;
+    if (S < target) n_chunks = (int)std::min<long long>(d.F, (target + S - 1) / std::max(S, 1));
+    const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
+    if (mode == MODE_MATRIX && hex && S >= 2 * sm_count()) n_chunks = 1;   // plain-store flush, no atomics
+    n_chunks = std::max(n_chunks, 1);
+    p.chunk_facets = (d.F + n_chunks - 1) / n_chunks;
+    p.n_chunks = (d.F + p.chunk_facets - 1) / p.chunk_facets;
+    // keep >= 16 warp items per block item when the chunk is short
+    p.msplit = 1;
+    if (p.chunk_facets < 16) p.msplit = std::max(1, std::min((16 + p.chunk_facets - 1) / p.chunk_facets, (d.M + 63) / 64));
+    p.msize = ((d.M + p.msplit - 1) / p.msplit + 31) / 32 * 32;
+    p.msplit = (d.M + p.msize - 1) / std::max(p.msize, 1);
+    p.n_items = (long long)S * p.n_chunks;
+    return p;
+}
+
+
+}  // namespace

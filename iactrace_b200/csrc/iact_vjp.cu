@@ -1,8 +1,361 @@
-// K6: vector-Jacobian product of render (placeholder until the backward kernel lands).
-#include "iact_common.cuh"
+// K6: vector-Jacobian product of `render` -- what jax.grad of reference core/render.py:174-220 yields
+// (SURVEY.md section 3.5), hand-derived per ray and accumulated with warp reductions.
+//
+// Differentiable leaves: stage-0 facet positions / rotations (Euler degrees) / perturbation_scale /
+// weights, the sources and values, and the sensor position / rotation.  Decisions (shadow mask,
+// pixel index, cube rounding, `where` guards) are piecewise constant and carry zero gradient, as in
+// JAX; with the hard sensors only d(value) flows, with the soft (Gaussian-splat) sensors
+// d(image)/d(x, y) flows too (sensors/square.py:144-172, sensors/hexagonal.py:264-314).
+//
+// Forward per ray (mirrors.py:64-79, render.py:129-155):
+//   p = R p_l + pos;  nw = R (n_l + scale d_l);  n = nw/|nw|;  d = (p - src)/|p - src|  |  src
+//   c = d.n;  r = d - 2 c n;  val = v (-c) / w * shadow
+//   t = (ns.ps - ns.p)/(ns.r);  h = p + t r - ps;  x = h.u1;  y = h.u2;  image += val * W(x, y)
+#include "iact_cull.cuh"
 
-extern "C" int iact_render_vjp(const IactScene*, const IactFacets*, const float*, const float*, int, int,
-                               const float*, const IactGrads*, void*) {
-    iact_set_error("iact_render_vjp: not implemented yet");
-    return IACT_ERR_UNSUPPORTED;
+namespace {
+
+struct GradsDev {
+    float *weights, *values, *sources;
+    float* facc;   // (F,13): dL/dR row-major (9), dL/dpos (3), dL/dscale (1)
+    float* sacc;   // 12: dL/d sensor pos (3), dL/d sensor R (9: u1,u2,n as columns -> row-major R)
+};
+
+// d(image . G)/d(val) and /d(x, y) for one hit.  Returns false if the hit contributes nothing.
+template <int SENS, typename LUT>
+__device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut, const float* __restrict__ G,
+                                               float x, float y, float& dval, float& dx, float& dy) {
+    dx = 0.f; dy = 0.f; dval = 0.f;
+    if (se.kind == IACT_SENSOR_SQUARE) {
+        const int pix = square_pixel(se, x, y);
+        if (pix < 0) return false;
+        dval = __ldg(G + pix);
+        return true;
+    }
+    if (se.kind == IACT_SENSOR_HEX) {
+        const int pix = hex_pixel(se, lut, x, y);
+        if (pix < 0) return false;
+        dval = __ldg(G + pix);
+        return true;
+    }
+    if (SENS == SENS_SQUARE) {
+        // image += val * sum_i g_i w_i / sum_i w_i,  w_i = exp(-((fx-ox)^2 + (fy-oy)^2) / (2 sigma^2))
+        const float xp = (x - se.x0) * se.inv_dx, yp = (y - se.y0) * se.inv_dy;
+        const float xb = floorf(xp), yb = floorf(yp);
+        const int K = se.ksize;
+        if (!(xb >= (float)(-K - 1) && xb <= (float)(se.W + K) && yb >= (float)(-K - 1) && yb <= (float)(se.H + K))) return false;
+        const float fx = xp - xb, fy = yp - yb;
+        const float inv_s2 = 1.0f / (se.sigma * se.sigma);
+        float D = 0.f, Nn = 0.f, gx = 0.f, gy = 0.f, wx = 0.f, wy = 0.f;
+        for (int oy = -K; oy <= K; ++oy)
+            for (int ox = -K; ox <= K; ++ox) {
+                const float ddx = fx - (float)ox, ddy = fy - (float)oy;
+                const float w = expf(-0.5f * (ddx * ddx + ddy * ddy) * inv_s2);
+                const float dwx = -w * ddx * inv_s2, dwy = -w * ddy * inv_s2;
+                const int xi = (int)xb + ox, yi = (int)yb + oy;
+                const float g = (xi >= 0 && xi < se.W && yi >= 0 && yi < se.H) ? __ldg(G + (size_t)yi * se.W + xi) : 0.f;
+                D += w; Nn += g * w; gx += g * dwx; gy += g * dwy; wx += dwx; wy += dwy;
+            }
+        const float invD = 1.0f / D;
+        dval = Nn * invD;
+        dx = (gx - dval * wx) * invD * se.inv_dx;
+        dy = (gy - dval * wy) * invD * se.inv_dy;
+        return true;
+    }
+    // soft hexagonal
+    float xg, yg; hex_grid_coords(se, x, y, xg, yg);
+    const float q = se.ax_qx * xg - se.ax_qy * yg, r = se.ax_ry * yg;
+    float qb, rb; hex_round(q, r, qb, rb);
+    if (!(fabsf(qb) < 1e6f && fabsf(rb) < 1e6f)) return false;
+    const float ddx = xg - se.size_sqrt3 * (qb + rb * 0.5f), ddy = yg - se.size_1p5 * rb;
+    const int K = se.ksize;
+    const float inv_sigma = 1.0f / se.sigma;
+    float D = 0.f, Nn = 0.f, gx = 0.f, gy = 0.f, wx = 0.f, wy = 0.f;
+    for (int oq = -K; oq <= K; ++oq)
+        for (int orr = -K; orr <= K; ++orr) {
+            if (max(max(abs(oq), abs(orr)), abs(oq + orr)) > K) continue;
+            const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
+            const float a = ddx - ox, b = ddy - oy;
+            const float aa = fabsf(a), ab = fabsf(b);
+            const float alt = 0.5f * aa + 0.8660254037844386f * ab;
+            const bool first = aa >= alt;
+            const float hd = fmaxf(aa, alt) * se.inv_inradius;
+            const float z = hd * inv_sigma;
+            const float w = expf(-0.5f * z * z);
+            // d hd / d a, d hd / d b  (sign(0) = 0, as jnp.abs)
+            const float sa = a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f), sb = b > 0.f ? 1.f : (b < 0.f ? -1.f : 0.f);
+            const float dha = (first ? sa : 0.5f * sa) * se.inv_inradius;
+            const float dhb = (first ? 0.f : 0.8660254037844386f * sb) * se.inv_inradius;
+            const float k = -w * z * inv_sigma;                 // dw/dhd
+            const float dwx = k * dha, dwy = k * dhb;
+            const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
+            const float g = pix >= 0 ? __ldg(G + pix) : 0.f;
+            D += w; Nn += g * w; gx += g * dwx; gy += g * dwy; wx += dwx; wy += dwy;
+        }
+    const float invD = 1.0f / D;
+    dval = Nn * invD;
+    const float dxg = (gx - dval * wx) * invD, dyg = (gy - dval * wy) * invD;
+    // (xg, yg) = Rot(-grid_rotation) (x - off):  xg = cr tx - sr ty, yg = sr tx + cr ty
+    dx = se.cr * dxg + se.sr * dyg;
+    dy = -se.sr * dxg + se.cr * dyg;
+    return true;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+template <int SRC, int SENS>
+__global__ void __launch_bounds__(256, 2)
+vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float* __restrict__ sources,
+           const float* __restrict__ values, const LaunchPlan plan, const FacetLists fl,
+           const float* __restrict__ G, const GradsDev gr) {
+    extern __shared__ __align__(16) float smem[];
+    ObsSmem ob;
+    const bool cull = sc.cull != 0;
+    stage_obstructions(sc, smem, ob, cull);
+    const int n_obs = ob.n_cyl + ob.n_rest;
+    float* p = smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri, cull);
+    const short* lut = nullptr;
+    if (SENS == SENS_HEX) {
+        short* l = reinterpret_cast<short*>(p);
+        for (int i = threadIdx.x; i < sc.sens.tq * sc.sens.tr; i += blockDim.x) l[i] = (short)sc.sens.lookup[i];
+        lut = l;
+        p += (sc.sens.tq * sc.sens.tr + 1) / 2;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    unsigned short* list = cull ? reinterpret_cast<unsigned short*>(p) + (size_t)warp * ((n_obs + 1) & ~1) : nullptr;
+    __syncthreads();
+
+    const int M = sc.M;
+    const SensDev& se = sc.sens;
+    const V3 ns = v3(se.nrm[0], se.nrm[1], se.nrm[2]), u1 = v3(se.u1[0], se.u1[1], se.u1[2]), u2 = v3(se.u2[0], se.u2[1], se.u2[2]);
+    const V3 ps = v3(se.pos[0], se.pos[1], se.pos[2]);
+    // sensor adjoints accumulate per lane over the whole block lifetime
+    V3 g_ps = v3(0.f, 0.f, 0.f), g_u1 = g_ps, g_u2 = g_ps, g_ns = g_ps;
+
+    for (long long item = blockIdx.x; item < plan.n_items; item += gridDim.x) {
+        const int s = (int)(item / plan.n_chunks), ch = (int)(item - (long long)s * plan.n_chunks);
+        const int f0 = ch * plan.chunk_facets, f1 = min(sc.F, f0 + plan.chunk_facets);
+        const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
+        const float sval = __ldg(values + s);
+        float g_val = 0.f;
+        V3 g_src = v3(0.f, 0.f, 0.f);
+
+        const int n_w = (f1 - f0) * plan.msplit;
+        for (int wi = warp; wi < n_w; wi += nwarps) {
+            const int fi = wi / plan.msplit, part = wi - fi * plan.msplit;
+            const int f = f0 + fi;
+            const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
+            int n_list = 0, n_list_cyl = 0;
+            if (cull) {
+                const Beam beam = make_beam<SRC>(__ldg(sc.bounds + f), src);
+                const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
+                if (cnt.x >= 0) n_list = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, n_list_cyl);
+                else            n_list = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, n_list_cyl);
+            }
+            const M33 R = euler_to_matrix(__ldg(fa.rotations + 3 * f), __ldg(fa.rotations + 3 * f + 1), __ldg(fa.rotations + 3 * f + 2));
+            const V3 pos = ld3(fa.positions + 3 * f);
+            const float scale = __ldg(fa.scale + f);
+            float gR[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            V3 g_pos = v3(0.f, 0.f, 0.f);
+            float g_scale = 0.f;
+
+            for (int m = m0 + lane; m < m1; m += 32) {
+                const size_t li = ((size_t)f * M + m) * 3;
+                const V3 pl = ld3(fa.points + li), nl = ld3(fa.normals + li), dl = ld3(fa.delta + li);
+                const float w = __ldg(fa.weights + (size_t)f * M + m);
+                // forward
+                const V3 o = mul(R, pl) + pos;
+                const V3 nq = nl + scale * dl;                      // local perturbed normal
+                const V3 nw = mul(R, nq);
+                const float inv_nw = 1.0f / sqrtf(dot(nw, nw));
+                const V3 n = inv_nw * nw;
+                V3 d; float inv_a = 0.f;
+                if (SRC == IACT_SOURCE_POINT) { d = o - src; inv_a = 1.0f / sqrtf(dot(d, d)); d = inv_a * d; }
+                else d = src;
+                if (occluded(ob, o, -d, list, n_list_cyl, n_list)) continue;
+                const float c = dot(d, n);
+                const V3 r = d - (2.0f * c) * n;
+                const float val = (sval * (-c)) / w;
+                const float B = dot(r, ns), ndoto = dot(o, ns);
+                if (fabsf(B) < 1e-10f) continue;
+                const float t = (se.ndotp - ndoto) / B;
+                if (t <= 0.f) continue;
+                const V3 h = o + t * r - ps;
+                const float x = dot(h, u1), y = dot(h, u2);
+                float dval, dx, dy;
+                if (!sensor_adjoint<SENS>(se, lut, G, x, y, dval, dx, dy)) continue;
+                // backward
+                const float xb = val * dx, yb = val * dy;           // dL/dx, dL/dy
+                V3 g_o = v3(0.f, 0.f, 0.f), g_r = g_o;
+                if (xb != 0.f || yb != 0.f) {
+                    const V3 g_h = xb * u1 + yb * u2;
+                    g_u1 = g_u1 + xb * h; g_u2 = g_u2 + yb * h;
+                    g_ps = g_ps - g_h;
+                    g_o = g_h;
+                    const float g_t = dot(g_h, r);
+                    g_r = t * g_h;
+                    const float gA = g_t / B, gB = -g_t * t / B;
+                    g_ns = g_ns + gA * (ps - o) + gB * r;
+                    g_ps = g_ps + gA * ns;
+                    g_o = g_o - gA * ns;
+                    g_r = g_r + gB * ns;
+                }
+                // val = v (-c)/w
+                float g_c = -dval * sval / w;
+                g_val += dval * (-c) / w;
+                if (gr.weights) atomicAdd(gr.weights + (size_t)f * M + m, -dval * val / w);
+                // r = d - 2 c n ; c = d.n
+                g_c += -2.0f * dot(g_r, n);
+                V3 g_d = g_r + g_c * n;
+                V3 g_n = (-2.0f * c) * g_r + g_c * d;
+                // n = nw/|nw| ; nw = R nq
+                const V3 g_nw = inv_nw * (g_n - dot(g_n, n) * n);
+                // d = a/|a| (point) | src (parallel)
+                if (SRC == IACT_SOURCE_POINT) {
+                    const V3 g_a = inv_a * (g_d - dot(g_d, d) * d);
+                    g_o = g_o + g_a;
+                    g_src = g_src - g_a;
+                } else {
+                    g_src = g_src + g_d;
+                }
+                // o = R pl + pos ; nw = R (nl + scale dl)
+                g_pos = g_pos + g_o;
+                g_scale += dot(g_nw, mul(R, dl));
+                gR[0] += g_o.x * pl.x + g_nw.x * nq.x; gR[1] += g_o.x * pl.y + g_nw.x * nq.y; gR[2] += g_o.x * pl.z + g_nw.x * nq.z;
+                gR[3] += g_o.y * pl.x + g_nw.y * nq.x; gR[4] += g_o.y * pl.y + g_nw.y * nq.y; gR[5] += g_o.y * pl.z + g_nw.y * nq.z;
+                gR[6] += g_o.z * pl.x + g_nw.z * nq.x; gR[7] += g_o.z * pl.y + g_nw.z * nq.y; gR[8] += g_o.z * pl.z + g_nw.z * nq.z;
+            }
+            // per-facet adjoints: warp reduce, one atomic per component
+            float* acc = gr.facc + (size_t)f * 13;
+#pragma unroll
+            for (int k = 0; k < 9; ++k) { const float v = warp_sum(gR[k]); if (lane == 0 && v != 0.f) atomicAdd(acc + k, v); }
+            { const float v = warp_sum(g_pos.x); if (lane == 0 && v != 0.f) atomicAdd(acc + 9, v); }
+            { const float v = warp_sum(g_pos.y); if (lane == 0 && v != 0.f) atomicAdd(acc + 10, v); }
+            { const float v = warp_sum(g_pos.z); if (lane == 0 && v != 0.f) atomicAdd(acc + 11, v); }
+            { const float v = warp_sum(g_scale); if (lane == 0 && v != 0.f) atomicAdd(acc + 12, v); }
+            __syncwarp();
+        }
+        // per-source adjoints
+        g_val = warp_sum(g_val); g_src.x = warp_sum(g_src.x); g_src.y = warp_sum(g_src.y); g_src.z = warp_sum(g_src.z);
+        if (lane == 0) {
+            if (gr.values && g_val != 0.f) atomicAdd(gr.values + s, g_val);
+            if (gr.sources) {
+                if (g_src.x != 0.f) atomicAdd(gr.sources + 3 * s, g_src.x);
+                if (g_src.y != 0.f) atomicAdd(gr.sources + 3 * s + 1, g_src.y);
+                if (g_src.z != 0.f) atomicAdd(gr.sources + 3 * s + 2, g_src.z);
+            }
+        }
+    }
+    // sensor adjoints: warp reduce then one atomic per warp and component
+    const float sv[12] = {g_ps.x, g_ps.y, g_ps.z,
+                          g_u1.x, g_u2.x, g_ns.x, g_u1.y, g_u2.y, g_ns.y, g_u1.z, g_u2.z, g_ns.z};   // dL/dR_s row-major
+#pragma unroll
+    for (int k = 0; k < 12; ++k) { const float v = warp_sum(sv[k]); if (lane == 0 && v != 0.f) atomicAdd(gr.sacc + k, v); }
+}
+
+// dL/d(euler degrees) from dL/dR for R = Rz(rot) Ry(tilt) Rx(tip)  (transforms.py:72-106)
+__device__ __forceinline__ void euler_adjoint(float tip, float tilt, float rot, const float* gR, float* out3) {
+    const float D2R = 0.017453292519943295f;
+    float sx, cx, sy, cy, sz, cz;
+    sincosf(tip * D2R, &sx, &cx); sincosf(tilt * D2R, &sy, &cy); sincosf(rot * D2R, &sz, &cz);
+    const float Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx}, dRx[9] = {0, 0, 0, 0, -sx, -cx, 0, cx, -sx};
+    const float Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy}, dRy[9] = {-sy, 0, cy, 0, 0, 0, -cy, 0, -sy};
+    const float Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1}, dRz[9] = {-sz, -cz, 0, cz, -sz, 0, 0, 0, 0};
+    auto mm = [](const float* A, const float* B, float* C) {
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    };
+    auto inner = [](const float* A, const float* B) { float s = 0.f; for (int i = 0; i < 9; ++i) s += A[i] * B[i]; return s; };
+    float T[9], U[9];
+    mm(Ry, dRx, T); mm(Rz, T, U); out3[0] = inner(gR, U) * D2R;
+    mm(dRy, Rx, T); mm(Rz, T, U); out3[1] = inner(gR, U) * D2R;
+    mm(Ry, Rx, T);  mm(dRz, T, U); out3[2] = inner(gR, U) * D2R;
+}
+
+__global__ void vjp_finalize_kernel(IactFacets fa, const float* __restrict__ facc, const float* __restrict__ sacc,
+                                    IactGrads out, float3 sensor_euler) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < fa.n_facets) {
+        const float* a = facc + (size_t)f * 13;
+        if (out.rotations) {
+            float e[3];
+            euler_adjoint(fa.rotations[3 * f], fa.rotations[3 * f + 1], fa.rotations[3 * f + 2], a, e);
+            for (int k = 0; k < 3; ++k) out.rotations[3 * f + k] += e[k];
+        }
+        if (out.positions) for (int k = 0; k < 3; ++k) out.positions[3 * f + k] += a[9 + k];
+        if (out.scale) out.scale[f] += a[12];
+    }
+    if (f == 0) {
+        if (out.sensor_position) for (int k = 0; k < 3; ++k) out.sensor_position[k] += sacc[k];
+        if (out.sensor_euler) {
+            float e[3];
+            euler_adjoint(sensor_euler.x, sensor_euler.y, sensor_euler.z, sacc + 3, e);
+            for (int k = 0; k < 3; ++k) out.sensor_euler[k] += e[k];
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets, const float* sources, const float* values,
+                               int n_sources, int source_type, const float* cotangent, const IactGrads* grads, void* stream) {
+    SceneDev d;
+    int rc = fill_scene(scene, d);
+    if (rc) return rc;
+    IACT_REQUIRE(facets && grads && cotangent, "null pointer");
+    IACT_REQUIRE(facets->n_facets == d.F && facets->n_samples == d.M, "facet tables do not match the scene");
+    IACT_REQUIRE(source_type == IACT_SOURCE_POINT || source_type == IACT_SOURCE_PARALLEL, "bad source_type");
+    if (d.n_stages > 0) {
+        iact_set_error("iact_render_vjp: gradients through optical stages >= 1 are not implemented");
+        return IACT_ERR_UNSUPPORTED;
+    }
+    const int S = n_sources;
+    if (S <= 0 || d.F == 0 || d.M == 0) return IACT_OK;
+    IACT_REQUIRE(sources && values, "null sources/values");
+    IACT_REQUIRE(facets->positions && facets->rotations && facets->scale && facets->points && facets->normals && facets->delta && facets->weights,
+                 "null facet table");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
+    LaunchPlan plan = make_plan(d, S, MODE_RENDER);
+    Scratch cull_scr, acc_scr;
+    FacetLists fl;
+    fl.ids = nullptr; fl.count = nullptr; fl.stride = 0;
+    if (d.cull && S >= 4) { rc = run_facet_cull(d, sources, S, source_type, cull_scr, fl, st); if (rc) return rc; }
+    const size_t acc_floats = (size_t)d.F * 13 + 12;
+    rc = acc_scr.alloc(acc_floats * sizeof(float), st);
+    if (rc) return rc;
+    IACT_CUDA(cudaMemsetAsync(acc_scr.ptr, 0, acc_floats * sizeof(float), st));
+    GradsDev gr;
+    gr.weights = grads->weights; gr.values = grads->values; gr.sources = grads->sources;
+    gr.facc = reinterpret_cast<float*>(acc_scr.ptr);
+    gr.sacc = gr.facc + (size_t)d.F * 13;
+
+    const int threads = 256;
+    size_t smem = (size_t)obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, d.cull != 0) * 4 + 16;
+    if (hex) smem += (size_t)((d.sens.tq * d.sens.tr + 1) / 2) * 4;
+    if (d.cull) smem += (size_t)(threads / 32) * ((d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri + 1) & ~1) * 2;
+    if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
+    auto launch = [&](auto kern) -> int {
+        if (smem > 48 * 1024) IACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        IACT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        const long long max_blocks = (long long)sm_count() * std::max(occ, 1);
+        const unsigned grid = (unsigned)std::max(1LL, std::min(plan.n_items, max_blocks));
+        kern<<<grid, threads, smem, st>>>(d, *facets, sources, values, plan, fl, cotangent, gr);
+        iact_count_launch();
+        return iact_check_cuda(cudaGetLastError(), "vjp_kernel launch");
+    };
+    if (source_type == IACT_SOURCE_POINT) rc = hex ? launch(vjp_kernel<IACT_SOURCE_POINT, SENS_HEX>) : launch(vjp_kernel<IACT_SOURCE_POINT, SENS_SQUARE>);
+    else rc = hex ? launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_HEX>) : launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_SQUARE>);
+    if (rc) return rc;
+    const float3 se = make_float3(scene->sensor.euler[0], scene->sensor.euler[1], scene->sensor.euler[2]);
+    vjp_finalize_kernel<<<(d.F + 127) / 128, 128, 0, st>>>(*facets, gr.facc, gr.sacc, *grads, se);
+    iact_count_launch();
+    return iact_check_cuda(cudaGetLastError(), "vjp_finalize_kernel launch");
 }

@@ -1,0 +1,131 @@
+"""Oracle for gradients: the single-mirror render restated in differentiable torch (float64, CPU).
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  Reverse-mode autodiff of this restatement is what
+``jax.grad`` of the reference's ``render`` (``iactrace/core/render.py:174-220``) produces for
+single-stage telescopes: the same chain ``transform_to_world`` (``telescope/mirrors.py:64-79``) ->
+directions (``render.py:129-133``) -> ``reflect`` (``core/reflection.py:5-19``) -> value
+(``render.py:141``) -> ``intersect_plane`` (``core/intersections.py:6-41``) -> ``accumulate``
+(``sensors/square.py:66-91,144-172``, ``sensors/hexagonal.py:174-194,264-314``), with the shadow mask
+and every index / rounding decision held constant (zero gradient), exactly as JAX treats
+``where`` / ``floor`` / ``round``.  The shadow mask itself comes from the NumPy oracle.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import trace as otrace
+from .scene import SQRT3, SQRT3_2, SQRT3_3
+
+DT = torch.float64
+
+
+def euler_to_matrix(e):
+    a = e * (math.pi / 180.0)
+    cx, sx, cy, sy, cz, sz = torch.cos(a[0]), torch.sin(a[0]), torch.cos(a[1]), torch.sin(a[1]), torch.cos(a[2]), torch.sin(a[2])
+    one, zero = torch.ones_like(cx), torch.zeros_like(cx)
+    Rx = torch.stack([torch.stack([one, zero, zero]), torch.stack([zero, cx, -sx]), torch.stack([zero, sx, cx])])
+    Ry = torch.stack([torch.stack([cy, zero, sy]), torch.stack([zero, one, zero]), torch.stack([-sy, zero, cy])])
+    Rz = torch.stack([torch.stack([cz, -sz, zero]), torch.stack([sz, cz, zero]), torch.stack([zero, zero, one])])
+    return Rz @ Ry @ Rx
+
+
+def _accumulate(s, x, y, v):
+    t = s["type"]
+    xn, yn = x.detach().numpy(), y.detach().numpy()
+    if t in ("square", "hexagonal"):
+        idx, valid, _ = otrace.pixel_index(s, xn, yn, np.float64)
+        n = int(np.prod(otrace.accumulator_shape(s)))
+        out = torch.zeros(n, dtype=DT)
+        out = out.index_add(0, torch.from_numpy(idx.astype(np.int64)), v * torch.from_numpy(valid.astype(np.float64)))
+        return out.reshape(otrace.accumulator_shape(s))
+    if t == "soft_square":
+        xp = (x - s["x0"]) / s["dx"]
+        yp = (y - s["y0"]) / s["dy"]
+        xb, yb = torch.floor(xp).detach(), torch.floor(yp).detach()
+        fx, fy = xp - xb, yp - yb
+        ox = torch.from_numpy(s["offset_x"].astype(np.float64))[None, :]
+        oy = torch.from_numpy(s["offset_y"].astype(np.float64))[None, :]
+        w = torch.exp(-0.5 * ((fx[:, None] - ox) ** 2 + (fy[:, None] - oy) ** 2) / s["sigma"] ** 2)
+        w = w / w.sum(1, keepdim=True)
+        xi = xb[:, None] + ox
+        yi = yb[:, None] + oy
+        valid = (xi >= 0) & (xi < s["width"]) & (yi >= 0) & (yi < s["height"])
+        idx = (yi.clamp(0, s["height"] - 1) * s["width"] + xi.clamp(0, s["width"] - 1)).long()
+        out = torch.zeros(s["height"] * s["width"], dtype=DT)
+        out = out.index_add(0, idx.reshape(-1), (v[:, None] * w * valid).reshape(-1))
+        return out.reshape(s["height"], s["width"])
+    if t == "soft_hexagonal":
+        ca, sa = math.cos(-s["grid_rotation"]), math.sin(-s["grid_rotation"])
+        tx, ty = x - s["grid_offset"][0], y - s["grid_offset"][1]
+        xg, yg = ca * tx - sa * ty, sa * tx + ca * ty
+        q = (SQRT3_3 * xg - yg / 3) / s["hex_size"]
+        r = (2 * yg / 3) / s["hex_size"]
+        qb, rb = otrace.axial_round(q.detach().numpy(), r.detach().numpy())
+        qb, rb = torch.from_numpy(qb), torch.from_numpy(rb)
+        dx = xg - s["hex_size"] * SQRT3 * (qb + rb / 2)
+        dy = yg - s["hex_size"] * 1.5 * rb
+        nq = torch.from_numpy(s["nb_q"].astype(np.float64))
+        nr = torch.from_numpy(s["nb_r"].astype(np.float64))
+        hx = dx[:, None] - (s["hex_size"] * SQRT3 * (nq + nr / 2))[None, :]
+        hy = dy[:, None] - (s["hex_size"] * 1.5 * nr)[None, :]
+        hd = torch.maximum(hx.abs(), 0.5 * hx.abs() + SQRT3_2 * hy.abs()) / s["hex_inradius"]
+        w = torch.exp(-0.5 * (hd / s["sigma"]) ** 2)
+        w = w / w.sum(1, keepdim=True)
+        qi = qb[:, None].numpy().astype(np.int64) + s["nb_q"][None, :]
+        ri = rb[:, None].numpy().astype(np.int64) + s["nb_r"][None, :]
+        pix, valid = otrace._hex_lookup(s, qi, ri)
+        out = torch.zeros(s["n_pixels"], dtype=DT)
+        return out.index_add(0, torch.from_numpy(pix.astype(np.int64)).reshape(-1),
+                             (v[:, None] * w * torch.from_numpy(valid.astype(np.float64))).reshape(-1))
+    raise ValueError(t)
+
+
+def render(scene, leaves, sources, values, source_type="point", sensor_idx=0):
+    """Differentiable render.  ``leaves`` = dict of float64 torch tensors (may require grad):
+    positions (F,3), rotations (F,3), scale (F,), weights (F,M,1), sensor_position (3,), sensor_rotation (3,);
+    ``sources`` (S,3) and ``values`` (S,) float64 torch tensors.  Single stage-0 group only."""
+    g = scene["groups"][0]
+    assert all(gr["stage"] == 0 for gr in scene["groups"]) and len(scene["groups"]) == 1
+    s = scene["sensors"][sensor_idx]
+    pts = torch.from_numpy(g["points"].astype(np.float64))
+    nrm = torch.from_numpy(g["normals"].astype(np.float64))
+    dlt = torch.from_numpy(g["delta"].astype(np.float64))
+    F = pts.shape[0]
+    Rs = euler_to_matrix(leaves["sensor_rotation"])
+    u1, u2, ns = Rs[:, 0], Rs[:, 1], Rs[:, 2]
+    ps = leaves["sensor_position"]
+    img = torch.zeros(otrace.accumulator_shape(s), dtype=DT)
+    # constant shadow mask from the NumPy oracle, evaluated at the current parameter values
+    sc_now = dict(scene)
+    gnow = dict(g, positions=leaves["positions"].detach().numpy(), rotations=leaves["rotations"].detach().numpy(),
+                scale=leaves["scale"].detach().numpy())
+    sc_now["groups"] = [gnow]
+    tp, tn, _ = otrace.transform_to_world(gnow, np.float64)
+    for f in range(F):
+        R = euler_to_matrix(leaves["rotations"][f])
+        p = pts[f] @ R.T + leaves["positions"][f]
+        nw = nrm[f] @ R.T + leaves["scale"][f] * (dlt[f] @ R.T)
+        n = nw / nw.norm(dim=-1, keepdim=True)
+        if source_type == "point":
+            d = p[None] - sources[:, None, :]
+            d = d / d.norm(dim=-1, keepdim=True)
+        else:
+            d = sources[:, None, :].expand(-1, p.shape[0], -1)
+        dnp = d.detach().numpy()
+        shadow = torch.from_numpy(otrace.check_occlusions(np.broadcast_to(tp[f][None], dnp.shape), -dnp,
+                                                          scene["obstructions"], np.float64))
+        c = (d * n[None]).sum(-1)
+        r = d - 2 * c[..., None] * n[None]
+        val = values[:, None] * (-c) / leaves["weights"][f][None, :, 0] * shadow
+        ndotd = (r * ns).sum(-1)
+        t = ((ns * ps).sum() - (p * ns).sum(-1)[None]) / ndotd
+        h = p[None] + t[..., None] * r - ps
+        x, y = (h * u1).sum(-1), (h * u2).sum(-1)
+        ok = (t > 0) & (ndotd.abs() >= 1e-10)
+        x = torch.where(ok, x, torch.full_like(x, 1e10))
+        y = torch.where(ok, y, torch.full_like(y, 1e10))
+        img = img + _accumulate(s, x.reshape(-1), y.reshape(-1), val.reshape(-1))
+    return img

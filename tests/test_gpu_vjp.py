@@ -1,0 +1,144 @@
+"""K6: the CUDA vector-Jacobian product (through torch.autograd over the C ABI) against reverse-mode
+autodiff of the float64 oracle -- i.e. against what jax.grad of the reference's render would give."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import iactrace_b200 as I
+from iactrace_b200.core import render
+from iactrace_b200.io import build_telescope, load_packed_config
+from iactrace_b200.sensors import DifferentiableHexagonalSensor, DifferentiableSquareSensor
+from iactrace_b200.telescope import operations as ops
+from oracle import trace_torch as ott
+from _bridge import to_oracle_scene, subset_config, point_grid, parallel_grid
+
+LEAVES = ("positions", "rotations", "scale", "weights", "sensor_position", "sensor_rotation", "sources", "values")
+
+
+def _make(sensor_kind, n_samples=12, step=110):
+    cfg = subset_config(load_packed_config("CT5"), mirror_step=step)
+    tel = build_telescope(cfg, I.MCIntegrator(n_samples), I.random.key(0)).apply_roughness(30)
+    hard = tel.sensors[0]
+    if sensor_kind == "soft_hex":
+        tel = tel.replace_sensor(DifferentiableHexagonalSensor(hard.position, hard.rotation, hard.hex_centers, 0.5, 1,
+                                                               grid=hard.grid_constants()), 0)
+    elif sensor_kind == "soft_square":
+        tel = tel.replace_sensor(DifferentiableSquareSensor(hard.position, hard.rotation, 64, 64, (-0.4, 0.4, -0.4, 0.4),
+                                                            sigma=0.8, kernel_size=2), 0)
+    return tel
+
+
+def _grads_cuda(tel, src, val, stype, G):
+    g = tel.mirror_groups[0]
+    leaf = dict(positions=g.positions.detach().clone().requires_grad_(True),
+                rotations=g.rotations.detach().clone().requires_grad_(True),
+                scale=g.perturbation_scale.detach().clone().requires_grad_(True),
+                weights=g.weights.detach().clone().requires_grad_(True),
+                sensor_position=tel.sensors[0].position.detach().clone().requires_grad_(True),
+                sensor_rotation=tel.sensors[0].rotation.detach().clone().requires_grad_(True),
+                sources=torch.tensor(src, device="cuda", requires_grad=True),
+                values=torch.tensor(val, device="cuda", requires_grad=True))
+    from iactrace_b200._util import replace
+    g2 = replace(g, positions=leaf["positions"], rotations=leaf["rotations"], perturbation_scale=leaf["scale"],
+                 weights=leaf["weights"])
+    s2 = replace(tel.sensors[0], position=leaf["sensor_position"], rotation=leaf["sensor_rotation"])
+    tel2 = replace(tel, mirror_groups=[g2], sensors=[s2] + tel.sensors[1:])
+    img = render(tel2, leaf["sources"], leaf["values"], stype, 0)
+    assert img.requires_grad
+    (img * torch.tensor(G, device="cuda", dtype=torch.float32).reshape(img.shape)).sum().backward()
+    return img.detach().cpu().numpy(), {k: v.grad.detach().cpu().numpy().astype(np.float64) for k, v in leaf.items()}
+
+
+def _grads_oracle(tel, src, val, stype, G):
+    sc = to_oracle_scene(tel)
+    g = sc["groups"][0]
+    T = lambda a: torch.tensor(np.asarray(a, np.float64), dtype=ott.DT, requires_grad=True)
+    leaves = dict(positions=T(g["positions"]), rotations=T(g["rotations"]), scale=T(g["scale"]), weights=T(g["weights"]),
+                  sensor_position=T(sc["sensors"][0]["position"]), sensor_rotation=T(sc["sensors"][0]["rotation"]))
+    s, v = T(src), T(val)
+    img = ott.render(sc, leaves, s, v, stype, 0)
+    (img * torch.tensor(G, dtype=ott.DT).reshape(img.shape)).sum().backward()
+    out = {k: t.grad.numpy() for k, t in leaves.items()}
+    out.update(sources=s.grad.numpy(), values=v.grad.numpy())
+    return img.detach().numpy(), out
+
+
+def _check(got, want, names, rtol):
+    for k in names:
+        a, b = got[k], want[k].reshape(got[k].shape)
+        scale = np.abs(b).max()
+        assert scale > 0, k
+        err = np.abs(a - b).max() / scale
+        assert err < rtol, f"{k}: max err / max |grad| = {err:.3e}"
+
+
+@pytest.mark.parametrize("stype", ["point", "parallel"])
+def test_hard_hex_sensor_value_path_gradients(stype):
+    """Hard sensors: only d(value) flows (pixel index is piecewise constant)."""
+    tel = _make("hard")
+    src = point_grid(2, 1.0) if stype == "point" else parallel_grid(2, 2.0)
+    val = np.array([1.0, 0.7, 1.3, 0.9], np.float32)
+    G = np.random.default_rng(1).normal(size=tel.sensors[0].n_pixels)
+    img, got = _grads_cuda(tel, src, val, stype, G)
+    oimg, want = _grads_oracle(tel, src, val, stype, G)
+    assert abs(img.sum() - oimg.sum()) < 1e-3 * oimg.sum()
+    names = ["rotations", "scale", "weights", "values"] + (["sources"] if stype == "parallel" else [])
+    _check(got, want, names, 2e-3)
+    # a far point source / a fixed sensor pose receive (numerically) no gradient through the value path
+    assert np.abs(got["sensor_position"]).max() == 0.0
+
+
+@pytest.mark.parametrize("kind,stype", [("soft_hex", "point"), ("soft_hex", "parallel"), ("soft_square", "parallel")])
+def test_soft_sensor_full_gradients(kind, stype):
+    tel = _make(kind)
+    src = point_grid(2, 1.0) if stype == "point" else parallel_grid(2, 2.0)
+    val = np.array([1.0, 0.7, 1.3, 0.9], np.float32)
+    shape = tel.sensors[0].get_accumulator_shape()
+    G = np.random.default_rng(2).normal(size=shape)
+    img, got = _grads_cuda(tel, src, val, stype, G)
+    oimg, want = _grads_oracle(tel, src, val, stype, G)
+    np.testing.assert_allclose(img, oimg, rtol=5e-3, atol=1e-4 * oimg.max())
+    names = ["rotations", "positions", "scale", "weights", "values", "sensor_position", "sensor_rotation"]
+    if stype == "parallel":
+        names.append("sources")
+    # f32 kernel vs f64 autodiff; a ray within rounding noise of a hex boundary changes its tap set: 1 %
+    _check(got, want, names, 1e-2)
+
+
+def test_alignment_fit_loss_decreases():
+    """BASELINE config 5 in miniature: gradient of 1/2 |img(theta) - img(theta*)|^2 w.r.t. facet tip/tilt."""
+    tel = _make("soft_hex", n_samples=24, step=60)
+    src = point_grid(2, 0.8)
+    val = np.ones(4, np.float32)
+    target = render(ops.apply_misalignment_to_group(tel, 0, 15, 10, I.random.key(4242)), src, val, "point", 0)
+    g = tel.mirror_groups[0]
+    rot = g.rotations.detach().clone().requires_grad_(True)
+    from iactrace_b200._util import replace
+
+    def loss_of(r):
+        t = replace(tel, mirror_groups=[replace(g, rotations=r)])
+        return 0.5 * ((render(t, src, val, "point", 0) - target) ** 2).sum()
+
+    l0 = loss_of(rot)
+    l0.backward()
+    grad = rot.grad.clone()
+    assert torch.isfinite(grad).all() and float(grad[:, :2].abs().max()) > 0
+    assert float(grad[:, 2].abs().max()) < 1e-3 * float(grad[:, :2].abs().max()) + 1e-6   # roll of a sphere cap: ~no effect
+    with torch.no_grad():
+        step = 1e-3 * float(l0) / float((grad ** 2).sum())
+        l1 = loss_of(rot - step * grad)
+    assert float(l1) < float(l0)
+
+
+def test_vjp_through_secondary_is_reported_unsupported():
+    from _bridge import cassegrain_config
+    tel = build_telescope(cassegrain_config(False), I.MCIntegrator(8), I.random.key(0))
+    g = tel.mirror_groups[0]
+    from iactrace_b200._util import replace
+    tel2 = replace(tel, mirror_groups=[replace(g, rotations=g.rotations.detach().clone().requires_grad_(True))] + tel.mirror_groups[1:])
+    d = np.array([[0.0, 0.0, -1.0]], np.float32)
+    img = render(tel2, d, np.ones(1, np.float32), "parallel", 0)
+    with pytest.raises(NotImplementedError):
+        img.sum().backward()
