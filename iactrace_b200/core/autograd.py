@@ -29,26 +29,26 @@ def needs_grad(tel, sources, values, sensor_idx) -> bool:
 class _Render(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tel, source_type, sensor_idx, src, val, *leaves):
-        from . import render as R
+        from .render import build_scene, _stype
         ctx.tel, ctx.source_type, ctx.sensor_idx = tel, source_type, sensor_idx
         ctx.save_for_backward(src, val)
         ctx.n_groups = (len(leaves) - 2) // 4
         with torch.no_grad():
             keep = []
-            sc, sensor = R.build_scene(tel, sensor_idx, keep)
+            sc, sensor = build_scene(tel, sensor_idx, keep)
             out = torch.empty(sensor.get_accumulator_shape(), dtype=torch.float32, device=src.device)
             if sc is None:
                 return out.zero_()
-            N.check(N.lib().iact_render(sc, N.ptr(src), N.ptr(val), src.shape[0], R._stype(source_type), N.ptr(out),
+            N.check(N.lib().iact_render(sc, N.ptr(src), N.ptr(val), src.shape[0], _stype(source_type), N.ptr(out),
                                         N.stream_ptr()), "render")
         return out
 
     @staticmethod
     def backward(ctx, g_img):
-        from . import render as R
+        from .render import build_scene, _stype, _get_stages
         tel, sensor_idx = ctx.tel, ctx.sensor_idx
         src, val = ctx.saved_tensors
-        stages = R._get_stages(tel.mirror_groups)
+        stages = _get_stages(tel.mirror_groups)
         g_img = contig(g_img.to(torch.float32))
         dev = src.device
         g_src = torch.zeros_like(src)
@@ -57,7 +57,7 @@ class _Render(torch.autograd.Function):
         g_srot = torch.zeros(3, device=dev)
         grads = []
         keep = []
-        sc, _ = R.build_scene(tel, sensor_idx, keep)
+        sc, _ = build_scene(tel, sensor_idx, keep)
         off = 0
         for g in stages.get(0, []):
             F, M = len(g), g.points.shape[1]
@@ -73,7 +73,7 @@ class _Render(torch.autograd.Function):
                 gr_struct = N.IactGrads(N.ptr(gp), N.ptr(gr), N.ptr(gs), N.ptr(gw), N.ptr(g_val), N.ptr(g_src),
                                         N.ptr(g_spos), N.ptr(g_srot))
                 N.check(N.lib().iact_render_vjp(sub, fa, N.ptr(src), N.ptr(val), src.shape[0],
-                                                R._stype(ctx.source_type), N.ptr(g_img), gr_struct, N.stream_ptr()),
+                                                _stype(ctx.source_type), N.ptr(g_img), gr_struct, N.stream_ptr()),
                         "render_vjp")
             grads += [gp, gr, gs, gw]
             off += F
