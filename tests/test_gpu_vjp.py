@@ -60,8 +60,9 @@ def _grads_oracle(tel, src, val, stype, G):
     s, v = T(src), T(val)
     img = ott.render(sc, leaves, s, v, stype, 0)
     (img * torch.tensor(G, dtype=ott.DT).reshape(img.shape)).sum().backward()
-    out = {k: t.grad.numpy() for k, t in leaves.items()}
-    out.update(sources=s.grad.numpy(), values=v.grad.numpy())
+    gnp = lambda t: t.grad.numpy() if t.grad is not None else np.zeros(tuple(t.shape))
+    out = {k: gnp(t) for k, t in leaves.items()}
+    out.update(sources=gnp(s), values=gnp(v))
     return img.detach().numpy(), out
 
 
