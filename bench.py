@@ -104,8 +104,16 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_rate(w, seconds_target=12.0, threads=0):
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_rate(w, seconds_target=12.0, threads=None):
     """Time the oracle's C restatement (all host threads) on a bounded sample of the workload."""
+    threads = threads or host_threads()      # explicit: torchrun exports OMP_NUM_THREADS=1
     from oracle import cport, prng, scene as oscene
     from iactrace_b200.io import load_packed_config
     cfg = load_packed_config(w["scene"])
@@ -134,10 +142,10 @@ def run_reference(args, w, rank, world):
     F, M = prep["tp"].shape[:2]
     rays_per_step = len(sel) * F * M
     for _ in range(args.warmup):
-        cport.render(prep, src[sel[:2]], val[sel[:2]], stype)
+        cport.render(prep, src[sel[:2]], val[sel[:2]], stype, threads=host_threads())
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cport.render(prep, src[sel], val[sel], stype)
+        cport.render(prep, src[sel], val[sel], stype, threads=host_threads())
     dt = time.perf_counter() - t0
     value = rays_per_step * args.steps / dt
     line = {"impl": "reference", "metric": "traced_rays_per_second", "value": value, "unit": "rays/s",

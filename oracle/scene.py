@@ -276,7 +276,7 @@ def load_yaml(path, n_samples, key=None, mode=prng.PARTITIONABLE, dt=f32):
 def apply_roughness(scene, arcsec):
     """operations.py:118-135."""
     out = copy.copy(scene)
-    sigma = f32(arcsec * f32(np.pi) / f32(180.0 * 3600.0))
+    sigma = f32(arcsec * np.pi / (180.0 * 3600.0))   # Python-double arithmetic, folded to f32 by jnp.full
     out["groups"] = [dict(g, scale=np.full(len(g["positions"]), sigma, f32)) for g in scene["groups"]]
     return out
 

@@ -1,0 +1,129 @@
+"""Pin the oracle on fixtures produced by EXECUTING the reference's own sources
+(tests/golden/make_golden.py; the reference runs on oracle/jaxshim because JAX is not installable)."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import prng, sample as osample, scene as oscene, trace as otrace
+from golden.cases import CASES, case_values
+
+GOLD = np.load(Path(__file__).parent / "golden" / "reference_golden.npz")
+META = json.loads((Path(__file__).parent / "golden" / "reference_golden.json").read_text())
+
+
+def _scene(name):
+    c = CASES[name]
+    sc = oscene.build_scene(c["cfg"](), c["M"], prng.key(c["seed"]), c["mode"])
+    if c["rough"]:
+        sc = oscene.apply_roughness(sc, c["rough"])
+    return sc
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_sampling_and_grouping_match_reference(name):
+    sc = _scene(name)
+    assert len(sc["groups"]) == META["cases"][name]["n_groups"]
+    for gi, g in enumerate(sc["groups"]):
+        k = f"{name}/group{gi}/"
+        assert np.array_equal(g["positions"], GOLD[k + "positions"]) and np.array_equal(g["rotations"], GOLD[k + "rotations"])
+        np.testing.assert_array_equal(g["scale"], GOLD[k + "perturbation_scale"])
+        assert g["points"].shape == GOLD[k + "points"].shape
+        if g["stage"] != 0:
+            assert g["points"].shape[1] == 0
+            continue
+        np.testing.assert_array_equal(g["points"], GOLD[k + "points"])
+        np.testing.assert_allclose(g["weights"], GOLD[k + "weights"], rtol=2e-7, atol=0)   # = normal_z / area * M
+        # normals/deltas: the oracle writes out the autodiff expression, the shim uses dual numbers: <= 1 ulp
+        np.testing.assert_allclose(g["normals"], GOLD[k + "normals"], rtol=0, atol=2e-7)
+        np.testing.assert_allclose(g["delta"], GOLD[k + "perturbation_delta"], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_render_paths_match_reference(name):
+    c = CASES[name]
+    sc = _scene(name)
+    val = case_values(name)
+    for si in c["sensors"]:
+        k = f"{name}/s{si}/"
+        pts, v = otrace.render_debug(sc, c["src"], val, c["stype"], si, np.float32)
+        gp, gv = GOLD[k + "debug_pts"], GOLD[k + "debug_vals"]
+        assert pts.shape == gp.shape
+        assert np.array_equal(v != 0, gv != 0)                      # identical shadow / hit decisions
+        np.testing.assert_allclose(v, gv, rtol=3e-6, atol=0)
+        ok = np.abs(gp[:, 0]) < 1e9
+        assert np.array_equal(ok, np.abs(pts[:, 0]) < 1e9)          # identical (1e10, 1e10) sentinels
+        assert np.abs(pts[ok] - gp[ok]).max() < 2e-5
+        img = otrace.render(sc, c["src"], val, c["stype"], si, np.float32)
+        gi = GOLD[k + "image"]
+        assert img.shape == gi.shape
+        assert abs(img.sum() - gi.sum()) <= 1e-5 * max(gi.sum(), 1e-9)
+        # per pixel, up to rays that sit on a pixel edge in one of the two evaluations
+        assert (np.abs(img - gi) > 1e-4 * gi.max()).mean() < 0.002
+        if k + "matrix" in GOLD:
+            M = otrace.render_response_matrix(sc, c["src"], val, c["stype"], si, np.float32)
+            assert M.shape == GOLD[k + "matrix"].shape
+            np.testing.assert_allclose(M.sum(1), GOLD[k + "matrix"].sum(1), rtol=1e-5)
+        s = sc["sensors"][si]
+        if s["type"] == "hexagonal":
+            hg = GOLD[k + "hexgrid"]
+            got = [s["hex_size"], s["hex_inradius"], s["grid_rotation"], s["grid_offset"][0], s["grid_offset"][1], s["q_min"], s["r_min"]]
+            np.testing.assert_allclose(got, hg, rtol=1e-6, atol=1e-9)
+            assert np.array_equal(s["lookup_table"], GOLD[k + "lookup"])
+
+
+def test_operations_match_reference():
+    c = CASES["ct3_point"]
+    sc = _scene("ct3_point")
+    t2 = oscene.apply_displacement_to_group(oscene.apply_misalignment_to_group(sc, 0, 15, 10, prng.key(4242)), 0, 0.02, prng.key(4242))
+    np.testing.assert_allclose(t2["groups"][0]["rotations"], GOLD["ops/misaligned_rotations"], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(t2["groups"][0]["positions"], GOLD["ops/displaced_positions"], rtol=0, atol=1e-7)
+    k = prng.split(prng.key(9), 1)[0]
+    np.testing.assert_array_equal(osample.sample_group(sc["groups"][0], k, 5)["points"], GOLD["ops/resampled_points"])
+    np.testing.assert_array_equal(prng.normal(prng.key(4242), 8), GOLD["unit/random_normal_key4242_n8"])
+    # soft sensors
+    val = case_values("ct3_point")
+    hard, lid = sc["sensors"][0], sc["sensors"][1]
+    soft = oscene.make_soft_hex_sensor(hard, 0.5, 1)
+    soft_sq = oscene.make_soft_square_sensor(lid["position"], lid["rotation"], 48, 32, (-0.768, 0.768, -0.512, 0.512), 0.7, 2)
+    sc2 = dict(sc, sensors=[soft, soft_sq])
+    np.testing.assert_allclose(otrace.render(sc2, c["src"], val, "point", 0, np.float32), GOLD["soft/hex_image"], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(otrace.render(sc2, c["src"], val, "point", 1, np.float32), GOLD["soft/square_image"], rtol=2e-4, atol=1e-6)
+
+
+def test_primitives_match_reference():
+    o, d = GOLD["unit/o"], GOLD["unit/d"]
+    f = np.float32
+
+    def cmp(t, key):
+        g = GOLD[key]
+        assert np.array_equal(np.isfinite(t), np.isfinite(g)), key
+        m = np.isfinite(g)
+        assert m.sum() >= 3, key
+        np.testing.assert_allclose(t[m], g[m], rtol=2e-5, err_msg=key)
+
+    cmp(otrace.intersect_cylinder(o, d, f([[-1, 0.5, 2]]), f([[2, -0.5, 4]]), f([0.8]))[:, 0], "unit/cylinder")
+    cmp(otrace.intersect_box(o, d, f([[-1, -2, 1]]), f([[1.5, 0.5, 3]]))[:, 0], "unit/box")
+    cmp(otrace.intersect_sphere(o, d, f([[0.5, 0.5, 3]]), f([1.7]))[:, 0], "unit/sphere")
+    th = np.deg2rad(30.0)
+    Rz = f([[[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]]])
+    cmp(otrace.intersect_oriented_box(o, d, f([[0.5, 0, 3]]), f([[1.5, 0.6, 1.0]]), Rz)[:, 0], "unit/obox")
+    cmp(otrace.intersect_triangle(o, d, f([[-4, -4, 3]]), f([[4, -3, 3.5]]), f([[0, 4, 2.5]]))[:, 0], "unit/triangle")
+    p = otrace.intersect_plane(o, d, f([0.1, -0.2, 5]), otrace.euler_to_matrix(f([3, -2, 20])))
+    g = GOLD["unit/plane"]
+    assert np.array_equal(p[:, 0] > 1e9, g[:, 0] > 1e9)
+    m = g[:, 0] < 1e9
+    np.testing.assert_allclose(p[m], g[m], rtol=1e-4, atol=1e-5)
+    for e, R in zip(f([[0, 0, 0], [90, 0, 0], [10, -20, 30], [180, 0, 0], [-7.5, 12.25, 359]]), GOLD["unit/euler"]):
+        np.testing.assert_allclose(otrace.euler_to_matrix(e), R, atol=2e-7)
+    r, c = otrace.reflect(d, np.roll(d, 1, axis=0))
+    np.testing.assert_allclose(r, GOLD["unit/reflect"], atol=1e-6)
+    np.testing.assert_allclose(c, GOLD["unit/reflect_cos"], atol=1e-6)
+    oo, dd = GOLD["unit/surf_o"], GOLD["unit/surf_d"]
+    cmp(otrace.intersect_conic(oo, dd, 0.05, -1.0), "unit/conic_t")
+    t, pt, n = otrace.surface_intersect(oo, dd, f([0.2, -0.1]), -0.05, -1.0, f([]))
+    cmp(t, "unit/surf_t")
+    m = np.isfinite(GOLD["unit/surf_t"])
+    np.testing.assert_allclose(pt[m], GOLD["unit/surf_pt"][m], atol=2e-6)
+    np.testing.assert_allclose(n[m], GOLD["unit/surf_n"][m], atol=2e-6)

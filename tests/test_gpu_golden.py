@@ -1,0 +1,102 @@
+"""The CUDA path (through the C ABI) against fixtures produced by EXECUTING the reference's own
+sources (tests/golden/make_golden.py): sampler, per-ray hits, images, response matrices, edits."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import iactrace_b200 as I
+from iactrace_b200 import random as R
+from iactrace_b200.core import render, render_debug, render_response_matrix
+from iactrace_b200.io import build_telescope
+from iactrace_b200.sensors import DifferentiableHexagonalSensor, DifferentiableSquareSensor
+from golden.cases import CASES, case_values
+
+GOLD = np.load(Path(__file__).parent / "golden" / "reference_golden.npz")
+
+
+def _tel(name):
+    c = CASES[name]
+    R.set_rng_mode(c["mode"])
+    try:
+        tel = build_telescope(c["cfg"](), I.MCIntegrator(c["M"]), R.key(c["seed"]))
+    finally:
+        R.set_rng_mode(R.PARTITIONABLE)
+    return tel.apply_roughness(c["rough"]) if c["rough"] else tel
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_sampler_matches_reference(name):
+    tel = _tel(name)
+    for gi, g in enumerate(tel.mirror_groups):
+        k = f"{name}/group{gi}/"
+        assert tuple(g.points.shape) == GOLD[k + "points"].shape
+        np.testing.assert_array_equal(g.perturbation_scale.cpu().numpy(), GOLD[k + "perturbation_scale"])
+        if g.optical_stage != 0:
+            continue
+        np.testing.assert_allclose(g.points.cpu().numpy(), GOLD[k + "points"], rtol=0, atol=3e-6)
+        np.testing.assert_allclose(g.normals.cpu().numpy(), GOLD[k + "normals"], rtol=0, atol=3e-6)
+        np.testing.assert_allclose(g.perturbation_delta.cpu().numpy(), GOLD[k + "perturbation_delta"], rtol=2e-5, atol=2e-5)
+        np.testing.assert_allclose(g.weights.cpu().numpy(), GOLD[k + "weights"], rtol=2e-6)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_render_matches_reference(name):
+    """Samples come from the CUDA sampler (within 3e-6 of the reference's), so hit coordinates carry
+    that through the optics: tolerance 1e-4 m on ~15-36 m lever arms, values 2e-5 relative."""
+    c = CASES[name]
+    tel = _tel(name)
+    val = case_values(name)
+    for si in c["sensors"]:
+        k = f"{name}/s{si}/"
+        xy, v = render_debug(tel, c["src"], val, c["stype"], si)
+        xy, v = xy.cpu().numpy(), v.cpu().numpy()
+        gp, gv = GOLD[k + "debug_pts"], GOLD[k + "debug_vals"]
+        assert xy.shape == gp.shape
+        flips = (v != 0) != (gv != 0)
+        assert flips.mean() <= 0.01, f"{flips.sum()} shadow/hit flips of {flips.size}"
+        both = ~flips & (gv != 0)
+        np.testing.assert_allclose(v[both], gv[both], rtol=2e-5)
+        ok = both & (np.abs(gp[:, 0]) < 1e9)
+        assert np.abs(xy[ok] - gp[ok]).max() < 1e-4
+        img = render(tel, c["src"], val, c["stype"], si).cpu().numpy()
+        gi = GOLD[k + "image"]
+        assert img.shape == gi.shape
+        lost = np.abs(gv[flips]).sum() + np.abs(v[flips]).sum()
+        assert abs(img.sum() - gi.sum()) <= 2e-4 * gi.sum() + lost
+        if k + "matrix" in GOLD:
+            M = render_response_matrix(tel, c["src"], val, c["stype"], si).cpu().numpy()
+            assert M.shape == GOLD[k + "matrix"].shape
+            np.testing.assert_allclose(M.sum(1), GOLD[k + "matrix"].sum(1), rtol=2e-4, atol=lost + 1e-7)
+        s = tel.sensors[si]
+        if hasattr(s, "hex_size"):
+            hg = GOLD[k + "hexgrid"]
+            got = [s.hex_size, s.hex_inradius, s.grid_rotation, s.grid_offset[0], s.grid_offset[1], s.q_min, s.r_min]
+            np.testing.assert_allclose(got, hg, rtol=1e-6, atol=1e-9)
+            assert np.array_equal(s.lookup_table.cpu().numpy(), GOLD[k + "lookup"])
+
+
+def test_operations_and_soft_sensors_match_reference():
+    c = CASES["ct3_point"]
+    tel = _tel("ct3_point")
+    t2 = tel.apply_misalignment_to_group(0, 15, 10, R.key(4242)).apply_displacement_to_group(0, 0.02, R.key(4242))
+    np.testing.assert_allclose(t2.mirror_groups[0].rotations.cpu().numpy(), GOLD["ops/misaligned_rotations"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(t2.mirror_groups[0].positions.cpu().numpy(), GOLD["ops/displaced_positions"], rtol=0, atol=1e-6)
+    t3 = tel.resample_mirrors(I.MCIntegrator(5), R.key(9))
+    np.testing.assert_allclose(t3.mirror_groups[0].points.cpu().numpy(), GOLD["ops/resampled_points"], rtol=0, atol=3e-6)
+    np.testing.assert_allclose(R.normal(R.key(4242), 8).cpu().numpy(), GOLD["unit/random_normal_key4242_n8"], rtol=3e-6, atol=1e-7)
+    hard, lid = tel.sensors[0], tel.sensors[1]
+    soft = DifferentiableHexagonalSensor(hard.position, hard.rotation, hard.hex_centers, sigma=0.5, kernel_size=1)
+    soft_sq = DifferentiableSquareSensor(lid.position, lid.rotation, 48, 32, (-0.768, 0.768, -0.512, 0.512), sigma=0.7, kernel_size=2)
+    t4 = tel.replace_sensor(soft, 0).replace_sensor(soft_sq, 1)
+    val = case_values("ct3_point")
+    for idx, key in ((0, "soft/hex_image"), (1, "soft/square_image")):
+        img = render(t4, c["src"], val, "point", idx).cpu().numpy()
+        g = GOLD[key]
+        assert img.shape == g.shape
+        np.testing.assert_allclose(img, g, rtol=5e-3, atol=2e-4 * g.max())
+        assert abs(img.sum() - g.sum()) < 1e-3 * g.sum()
