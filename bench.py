@@ -46,6 +46,8 @@ WORKLOADS = {
     "ct5_point_4096x4096_hex": dict(scene="CT5", M=4096, grid=("point", 64, 1.5), sensor=0, mode="render"),
     "ct3_matrix_64x64_M64": dict(scene="CT3", M=64, grid=("parallel", 64, 5.5), sensor=0, mode="matrix", roughness=24, seed=42),
     "ct3_matrix_64x64_M1000": dict(scene="CT3", M=1000, grid=("parallel", 64, 5.5), sensor=0, mode="matrix", roughness=24, seed=42),
+    # BASELINE config 3: Cassegrain (examples/Cassegrain.ipynb cell 3) + synthetic obstructions, 1e9 rays
+    "cassegrain_1e9": dict(scene="cassegrain", M=16667, grid=("stars", 10000, 3.0), sensor=0, mode="render"),
 }
 DEFAULT_WORKLOAD = "ct5_point_4096x115_hex"
 
@@ -53,6 +55,11 @@ DEFAULT_WORKLOAD = "ct5_point_4096x115_hex"
 def make_sources(w, rank=0):
     from _bridge import point_grid, parallel_grid
     kind, n_side, ang = w["grid"]
+    if kind == "stars":  # Cassegrain.ipynb cell 8: uniform directions in a 3 deg box, z = -1, normalised
+        rng = np.random.default_rng(42 + rank)
+        f = np.deg2rad(ang)
+        d = np.stack([rng.uniform(-f / 2, f / 2, n_side), rng.uniform(-f / 2, f / 2, n_side), -np.ones(n_side)], 1)
+        return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32), "parallel"
     if kind == "point":
         src = point_grid(n_side, ang)
         if rank:  # rank-specific sub-pixel shift of the field angles (weak scaling: distinct work per rank)
@@ -63,6 +70,14 @@ def make_sources(w, rank=0):
         src[:, 0] += np.float32(5e-5 * rank)
         src /= np.linalg.norm(src, axis=1, keepdims=True)
     return src.astype(np.float32), "parallel"
+
+
+def load_scene_config(name):
+    if name == "cassegrain":
+        from _bridge import cassegrain_config
+        return cassegrain_config(True)
+    from iactrace_b200.io import load_packed_config
+    return load_packed_config(name)
 
 
 class ClockSampler:
@@ -77,7 +92,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "25", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -112,46 +127,54 @@ def host_threads():
 
 
 def cpu_reference_rate(w, seconds_target=12.0, threads=None):
-    """Time the oracle's C restatement (all host threads) on a bounded sample of the workload."""
+    """Time the oracle (CPU restatement of the reference algorithm) on a bounded sample of the workload:
+    the C/OpenMP port on all host threads where it applies (single-stage telescopes), else the NumPy form."""
     threads = threads or host_threads()      # explicit: torchrun exports OMP_NUM_THREADS=1
-    from oracle import cport, prng, scene as oscene
-    from iactrace_b200.io import load_packed_config
-    cfg = load_packed_config(w["scene"])
+    from oracle import cport, prng, scene as oscene, trace as otrace
+    cfg = load_scene_config(w["scene"])
+    src, stype = make_sources(w)
+    val = np.ones(len(src), np.float32)
+    if any(m.get("stage", 0) for m in cfg["mirrors"]):
+        sc = oscene.build_scene(cfg, min(w["M"], 64), prng.key(w.get("seed", 0)))
+        F = sum(len(g["positions"]) for g in sc["groups"] if g["stage"] == 0)
+        M = sc["groups"][0]["points"].shape[1]
+        n = max(2, min(len(src), int(seconds_target * 2e4 / (F * M))))
+        sel = np.arange(n)
+        render = lambda idx: otrace.render(sc, src[idx], val[idx], stype, w["sensor"], np.float32)
+        t0 = time.perf_counter(); render(sel); dt = time.perf_counter() - t0
+        rays = n * F * M
+        return rays / dt, 1, f"NumPy oracle: {n} of {len(src)} sources x {F} facets x {M} samples ({rays:.3g} rays, {dt:.1f} s)", (render, sel, rays)
     sc = oscene.build_scene(cfg, min(w["M"], 115), prng.key(w.get("seed", 0)))
     if w.get("roughness"):
         sc = oscene.apply_roughness(sc, w["roughness"])
     prep = cport.prepare(sc, w["sensor"])
-    src, stype = make_sources(w)
-    val = np.ones(len(src), np.float32)
     F, M = prep["tp"].shape[:2]
+    render = lambda idx: cport.render(prep, src[idx], val[idx], stype, threads=threads)
     # calibrate on 2 sources, then size the sample for ~seconds_target
-    t0 = time.perf_counter(); _, nt = cport.render(prep, src[:2], val[:2], stype, threads=threads); dt = time.perf_counter() - t0
+    t0 = time.perf_counter(); _, nt = render(np.arange(2)); dt = time.perf_counter() - t0
     n = int(max(2, min(len(src), seconds_target / max(dt / 2, 1e-6))))
     sel = np.linspace(0, len(src) - 1, n).astype(int)
-    t0 = time.perf_counter(); cport.render(prep, src[sel], val[sel], stype, threads=threads); dt = time.perf_counter() - t0
+    t0 = time.perf_counter(); render(sel); dt = time.perf_counter() - t0
     rays = n * F * M
-    return rays / dt, nt, f"{n} of {len(src)} sources x {F} facets x {M} samples ({rays:.3g} rays, {dt:.1f} s)", (prep, src, val, stype, sel)
+    return rays / dt, nt, f"C/OpenMP oracle: {n} of {len(src)} sources x {F} facets x {M} samples ({rays:.3g} rays, {dt:.1f} s)", (render, sel, rays)
 
 
 def run_reference(args, w, rank, world):
-    """--impl reference: the reference algorithm's CPU implementation (oracle C port) on host cores."""
+    """--impl reference: the reference algorithm's CPU implementation (the oracle) on the host cores."""
     if rank != 0:
         return
-    rate, nt, sample, (prep, src, val, stype, sel) = cpu_reference_rate(w, seconds_target=2.0)
-    from oracle import cport
-    F, M = prep["tp"].shape[:2]
-    rays_per_step = len(sel) * F * M
+    rate, nt, sample, (render, sel, rays_per_step) = cpu_reference_rate(w, seconds_target=2.0)
     for _ in range(args.warmup):
-        cport.render(prep, src[sel[:2]], val[sel[:2]], stype, threads=host_threads())
+        render(sel[:2])
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cport.render(prep, src[sel], val[sel], stype, threads=host_threads())
+        render(sel)
     dt = time.perf_counter() - t0
     value = rays_per_step * args.steps / dt
     line = {"impl": "reference", "metric": "traced_rays_per_second", "value": value, "unit": "rays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "note": "reference = JAX (not installable here); timed: oracle C restatement of the reference algorithm, OpenMP, brute-force obstruction tests as in the reference"},
+            "config": {"workload": args.workload, "note": "reference = JAX (not installable here); timed: the oracle's CPU restatement of the reference algorithm, brute-force obstruction tests as in the reference"},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": nt, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -160,7 +183,7 @@ def run_reference(args, w, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -190,11 +213,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    tel = build_telescope(load_packed_config(w["scene"]), I.MCIntegrator(w["M"]), I.random.key(w.get("seed", 0)))
+    tel = build_telescope(load_scene_config(w["scene"]), I.MCIntegrator(w["M"]), I.random.key(w.get("seed", 0)))
     if w.get("roughness"):
         tel = tel.apply_roughness(w["roughness"])
     src_np, stype = make_sources(w, rank)
     val_np = np.ones(len(src_np), np.float32)
+    if w["grid"][0] == "stars":
+        val_np = (10 ** (-10 * np.random.default_rng(4242).uniform(size=len(src_np)))).astype(np.float32)
     src_host = torch.from_numpy(src_np).pin_memory()
     val_host = torch.from_numpy(val_np).pin_memory()
     src_dev, val_dev = src_host.to(dev), val_host.to(dev)
@@ -289,8 +314,11 @@ def main():
         n_cyl = sc.n_cyl
         n_oth = sc.n_box + sc.n_sph + sc.n_obox + sc.n_tri
         f_fixed = F_FIXED[(sensor_kind, stype)]
-        f_brute = f_fixed + F_CYL * n_cyl + F_BOX * n_oth
-        f_culled = f_fixed + F_CYL * n_cyl_kept / max(n_pairs, 1) + F_BOX * n_oth_kept / max(n_pairs, 1)
+        n_sec = sum(len(g) for g in tel.mirror_groups if g.optical_stage > 0)
+        # each extra optical stage: 530 flop per (ray, mirror) + a brute-force shadow test of that leg (App. C)
+        f_stage = n_sec * 530 + (F_CYL * n_cyl + F_BOX * n_oth if n_sec else 0)
+        f_brute = f_fixed + F_CYL * n_cyl + F_BOX * n_oth + f_stage
+        f_culled = f_fixed + F_CYL * n_cyl_kept / max(n_pairs, 1) + F_BOX * n_oth_kept / max(n_pairs, 1) + f_stage
         kern_s = total_ms * 1e-3 / args.steps
         achieved = rays_per_step * f_culled / kern_s / 1e12
         out_bytes = (out.numel() * 4) + h2d  # algorithmic HBM bytes per launch: image + sources (tables are L2-resident)
