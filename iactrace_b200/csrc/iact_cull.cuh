@@ -236,6 +236,7 @@ int fill_scene(const IactScene* s, SceneDev& d) {
 size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
     const int n_obs = d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri;
     size_t fl = obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, d.cull != 0);
+    fl += stage_floats(d);
     if (sens == SENS_HEX) {
         if (mode != MODE_DEBUG) fl += d.sens.npix;
         fl += (d.sens.tq * d.sens.tr + 1) / 2;

@@ -90,7 +90,7 @@ __device__ __forceinline__ void warp_hist_add(float* hist, int pix, float val) {
 
 // ---------------------------------------------------------------- the kernel
 #ifndef IACT_MIN_BLOCKS
-#define IACT_MIN_BLOCKS 3
+#define IACT_MIN_BLOCKS 4
 #endif
 template <int SRC, int SENS, int MODE, bool STAGES>
 __global__ void __launch_bounds__(256, STAGES ? 1 : IACT_MIN_BLOCKS)
@@ -103,6 +103,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     stage_obstructions(sc, smem, ob, cull);
     const int n_obs = ob.n_cyl + ob.n_rest;
     float* p = smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri, cull);
+    StageSmem stages[IACT_MAX_STAGES];
+    if (STAGES) { stage_mirrors(sc, p, stages); p += stage_floats(sc); }
     float* hist = nullptr;
     const short* lut = nullptr;
     if (SENS == SENS_HEX) {
@@ -152,8 +154,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 V3 d;
                 if (SRC == IACT_SOURCE_POINT) {
                     d = o - src;
-                    const float inv = 1.0f / sqrtf(dot(d, d));
-                    d = inv * d;
+                    d = frsqrt_nr(dot(d, d)) * d;
                 } else {
                     d = src;
                 }
@@ -162,9 +163,9 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 // render.py:140-141, reflection.py:17-19
                 const float c = dot(d, n);
                 d = d - (2.0f * c) * n;
-                float val = blocked ? 0.f : (sval * (-c)) / a.w;
+                float val = blocked ? 0.f : (sval * (-c)) * a.w;         // a.w = 1/weight (transform_kernel)
                 if (STAGES) {
-                    for (int st = 0; st < sc.n_stages; ++st) reflect_at_stage(sc.stages[st], ob, o, d, val);
+                    for (int st = 0; st < sc.n_stages; ++st) reflect_at_stage(stages[st], ob, o, d, val);
                 }
                 // render.py:152-155
                 float x, y;

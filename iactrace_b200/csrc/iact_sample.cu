@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) transform_kernel(const IactFacets fa, int
         const V3 pw = rp + pos;
         V3 nw = mul(R, nl) + scale * mul(R, dl);
         nw = (1.0f / sqrtf(dot(nw, nw))) * nw;
-        out[2 * m] = make_float4(pw.x, pw.y, pw.z, fa.weights[(size_t)f * M + m]);
+        out[2 * m] = make_float4(pw.x, pw.y, pw.z, 1.0f / fa.weights[(size_t)f * M + m]);   // value = v cos / w (render.py:141)
         out[2 * m + 1] = make_float4(nw.x, nw.y, nw.z, 0.f);
         const V3 dd = pw - pos;
         maxd2 = fmaxf(maxd2, dot(dd, dd));

@@ -96,7 +96,7 @@ typedef struct IactSensor {
 /* Everything a render needs.  `world`/`bounds` come from iact_transform_to_world. */
 typedef struct IactScene {
     int32_t      n_facets, n_samples;
-    const float* world;    /* device (F, M, 8): px,py,pz,weight, nx,ny,nz,0 */
+    const float* world;    /* device (F, M, 8): px,py,pz,1/weight, nx,ny,nz,0 */
     const float* bounds;   /* device (F, 4): bounding sphere of the facet's world points */
     /* obstruction groups in the reference's fixed order (obstructions.py:258-278) */
     int32_t n_cyl;  const float *cyl_p1, *cyl_p2, *cyl_r;       /* (K,3)(K,3)(K,)   */
@@ -162,7 +162,7 @@ int iact_random_uniform(const uint32_t key[2], int rng_mode, int n, float lo, fl
 /* MirrorGroup.transform_to_world (telescope/mirrors.py:64-79), writing rows
  * [facet_offset, facet_offset + n_facets) of the packed world table + bounds. */
 int iact_transform_to_world(const IactFacets* facets, int facet_offset,
-                            float* world /*device (Ftot,M,8)*/, float* bounds /*device (Ftot,4)*/, void* stream);
+                            float* world /*device (Ftot,M,8): px,py,pz,1/w, nx,ny,nz,0*/, float* bounds /*device (Ftot,4)*/, void* stream);
 
 /* render (core/render.py:174-220).  out_image: device (H,W) or (P,), OVERWRITTEN. */
 int iact_render(const IactScene* scene, const float* sources /*device (S,3)*/, const float* values /*device (S,)*/,
