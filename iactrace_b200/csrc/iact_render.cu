@@ -93,7 +93,7 @@ __device__ __forceinline__ void warp_hist_add(float* hist, int pix, float val) {
 #define IACT_MIN_BLOCKS 4
 #endif
 template <int SRC, int SENS, int MODE, bool STAGES>
-__global__ void __launch_bounds__(256, STAGES ? 1 : IACT_MIN_BLOCKS)
+__global__ void __launch_bounds__(256, STAGES ? 2 : IACT_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
              const LaunchPlan plan, const FacetLists fl, float* __restrict__ out, float* __restrict__ out_val,
              int* __restrict__ out_pix) {
@@ -103,8 +103,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     stage_obstructions(sc, smem, ob, cull);
     const int n_obs = ob.n_cyl + ob.n_rest;
     float* p = smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri, cull);
-    StageSmem stages[IACT_MAX_STAGES];
-    if (STAGES) { stage_mirrors(sc, p, stages); p += stage_floats(sc); }
+    const float* stage_rec = p;
+    if (STAGES) { stage_mirrors(sc, p); p += stage_floats(sc); }
     float* hist = nullptr;
     const short* lut = nullptr;
     if (SENS == SENS_HEX) {
@@ -165,7 +165,11 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 d = d - (2.0f * c) * n;
                 float val = blocked ? 0.f : (sval * (-c)) * a.w;         // a.w = 1/weight (transform_kernel)
                 if (STAGES) {
-                    for (int st = 0; st < sc.n_stages; ++st) reflect_at_stage(stages[st], ob, o, d, val);
+                    const float* rec = stage_rec;
+                    for (int st = 0; st < sc.n_stages; ++st) {
+                        reflect_at_stage(sc.stages[st].n, rec, sc.stages[st].verts, ob, o, d, val);
+                        rec += (size_t)sc.stages[st].n * STAGE_REC;
+                    }
                 }
                 // render.py:152-155
                 float x, y;

@@ -21,8 +21,14 @@ class _SensorBase:
         raise NotImplementedError
 
     def _pose(self, s):
-        pos = self.position.detach().cpu().tolist()
-        rot = self.rotation.detach().cpu().tolist()
+        # host copy of the pose, cached per tensor version: reading it back on every render would
+        # synchronise the stream
+        sig = (self.position.data_ptr(), self.position._version, self.rotation.data_ptr(), self.rotation._version)
+        cached = self.__dict__.get("_pose_cache")
+        if cached is None or cached[0] != sig:
+            cached = (sig, self.position.detach().cpu().tolist(), self.rotation.detach().cpu().tolist())
+            self.__dict__["_pose_cache"] = cached
+        _, pos, rot = cached
         for i in range(3):
             s.position[i] = pos[i]
             s.euler[i] = rot[i]

@@ -123,6 +123,52 @@ def test_culling_is_exact():
         assert 0.0 < shadowed < 0.9
 
 
+def test_culling_fuzz_random_scenes():
+    """Random obstruction clouds of all five types, near / far / inside-the-structure sources and
+    parallel directions: the hierarchical culling must reproduce the brute-force kernel bit for bit."""
+    from iactrace_b200.core import Box, Cylinder, OrientedBox, Sphere, Triangle, group_obstructions
+    rng = np.random.default_rng(2024)
+    base = _tel("CT5", 33, step=7)
+    total_shadowed = 0
+    for trial in range(6):
+        obs = []
+        for _ in range(40):
+            a = rng.uniform([-16, -12, 0.5], [16, 12, 38])
+            b = a + rng.normal(size=3) * rng.uniform(0.2, 12)
+            obs.append(Cylinder(a, b, float(rng.uniform(0.01, 0.4))))
+        for _ in range(6):
+            a = rng.uniform([-14, -10, 2], [14, 10, 38])
+            obs.append(Box(a, a + rng.uniform(0.1, 2.0, 3) * rng.choice([-1, 1], 3)))
+            obs.append(Sphere(rng.uniform([-14, -10, 2], [14, 10, 38]), float(rng.uniform(0.05, 1.0))))
+            q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+            obs.append(OrientedBox(rng.uniform([-14, -10, 2], [14, 10, 38]), rng.uniform(0.1, 1.5, 3), q))
+            v0 = rng.uniform([-14, -10, 2], [14, 10, 38])
+            obs.append(Triangle(v0, v0 + rng.normal(size=3) * 2, v0 + rng.normal(size=3) * 2))
+        tel = I.Telescope(base.mirror_groups, group_obstructions(obs), base.sensors)
+        if trial % 2 == 0:
+            stype = "point"
+            far = point_grid(2, 2.0)
+            near = rng.uniform([-20, -15, 5], [20, 15, 120], (6, 3)).astype(np.float32)    # some inside the structure
+            src = np.concatenate([far, near]).astype(np.float32)
+        else:
+            stype = "parallel"
+            d = rng.normal(size=(8, 3)) * [0.3, 0.3, 0.1] + [0, 0, -1]
+            src = (d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(0.5, 2.0, (8, 1))).astype(np.float32)
+        val = np.ones(len(src), np.float32)
+        res = []
+        for cull in (True, False):
+            Rm.cull_obstructions = cull
+            try:
+                xy, v = render_debug(tel, src, val, stype, 0)
+                res.append((xy.cpu().numpy(), v.cpu().numpy()))
+            finally:
+                Rm.cull_obstructions = True
+        assert np.array_equal(res[0][1], res[1][1]), f"trial {trial}: {np.sum(res[0][1] != res[1][1])} rays differ"
+        assert np.array_equal(res[0][0], res[1][0])
+        total_shadowed += int((res[0][1] == 0).sum())
+    assert total_shadowed > 1000
+
+
 def test_response_matrix_rows_are_single_source_images():
     """BASELINE config 4 geometry: CT3 + roughness 24", parallel grid; row i == render of source i."""
     tel = _tel("CT3", 16, step=4, seed=42).apply_roughness(24)
