@@ -132,7 +132,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
 
         const int n_w = (f1 - f0) * plan.msplit;
         for (int wi = warp; wi < n_w; wi += nwarps) {
-            const int fi = wi / plan.msplit, part = wi - fi * plan.msplit;
+            int fi = wi, part = 0;
+            if (plan.msplit > 1) { fi = wi / plan.msplit; part = wi - fi * plan.msplit; }
             const int f = f0 + fi;
             const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
             int n_list = 0, n_list_cyl = 0;

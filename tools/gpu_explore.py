@@ -77,6 +77,25 @@ def main():
         print(f"CT3 response matrix 64x64 M={M}: {med:.2f} ms -> {rays/med/1e6:.1f} Grays/s")
         med, mn = timeit(lambda: render(tel, src, val, "parallel", 0))
         print(f"CT3 render 64x64 M={M}: {med:.2f} ms -> {rays/med/1e6:.1f} Grays/s")
+    # BASELINE config 5: CT5 + soft hex sensor, S=64, M=115: forward + VJP w.r.t. facet rotations
+    from iactrace_b200.sensors import DifferentiableHexagonalSensor
+    from iactrace_b200._util import replace
+    tel = build_telescope(ct5, I.MCIntegrator(115), I.random.key(0))
+    hard = tel.sensors[0]
+    tel = tel.replace_sensor(DifferentiableHexagonalSensor(hard.position, hard.rotation, hard.hex_centers, 0.5, 1, grid=hard.grid_constants()), 0)
+    for S_side in (8, 64):
+        src = torch.from_numpy(point_grid(S_side, 1.5)).cuda(); val = torch.ones(len(src), device="cuda")
+        target = render(tel.apply_misalignment_to_group(0, 15, 10, I.random.key(4242)), src, val, "point", 0)
+        g = tel.mirror_groups[0]
+        rot = g.rotations.detach().clone().requires_grad_(True)
+        def fwd_bwd():
+            rot.grad = None
+            t = replace(tel, mirror_groups=[replace(g, rotations=rot)])
+            loss = 0.5 * ((render(t, src, val, "point", 0) - target) ** 2).sum()
+            loss.backward()
+        med, mn = timeit(fwd_bwd)
+        rays = len(src) * 876 * 115
+        print(f"CT5 config5 soft-hex S={len(src)}: forward+VJP {med:.2f} ms -> {rays/med/1e6:.1f} Grays/s (fwd+bwd), |grad| max {float(rot.grad.abs().max()):.3g}")
     tel = build_telescope(ct3, I.MCIntegrator(1000), I.random.key(0))
     s1 = torch.tensor([[0., 0., 1e10]], device="cuda"); v1 = torch.ones(1, device="cuda")
     for sensor in (0, 1):
