@@ -101,6 +101,115 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
     return true;
 }
 
+
+// ---------------------------------------------------------------- optical stages >= 1
+// Forward selection of the mirror a ray hits in one stage (same arithmetic as reflect_at_stage, plus
+// the index and ray parameter needed by the backward pass).
+__device__ __forceinline__ bool stage_select(int n_mirrors, const float* rec, const float* verts, V3 o, V3 d,
+                                             int& best_mi, float& best_t) {
+    best_t = INFINITY; best_mi = -1;
+    for (int mi = 0; mi < n_mirrors; ++mi) {
+        const float* r = rec + (size_t)mi * STAGE_REC;
+        const V3 pos = v3(r[0], r[1], r[2]);
+        M33 R;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R.m[k] = r[24 + k];
+        SurfRef s;
+        s.c = r[8]; s.k = r[9]; s.kc2 = r[33]; s.n_asph = (int)r[10]; s.asph = r + 11;
+        V3 pl, nl;
+        float t = surface_intersect(s, r[6], r[7], mulT(R, o - pos), mulT(R, d), pl, nl);
+        bool inside;
+        if (r[19] == 0.f) {
+            inside = pl.x * pl.x + pl.y * pl.y <= r[20] * r[20];
+        } else {
+            const int nv = (int)r[21];
+            const float* V = verts + 2 * (size_t)r[22];
+            inside = true;
+            for (int i = 0; i < nv; ++i) {
+                const int j = (i + 1 == nv) ? 0 : i + 1;
+                const float cr = (V[2 * j] - V[2 * i]) * (pl.y - V[2 * i + 1]) - (V[2 * j + 1] - V[2 * i + 1]) * (pl.x - V[2 * i]);
+                inside = inside && (cr >= 0.f);
+            }
+        }
+        if (!inside) t = INFINITY;
+        if (t < best_t) { best_t = t; best_mi = mi; }
+    }
+    return best_t < IACT_TMAX;
+}
+
+// Local geometry of mirror record r at ray parameter t: hit point, unit normal, first and second
+// derivatives of the sag (surfaces.py:25-58; d sag/d r2 = c / (2 s), s = sqrt(1 - (1+k) c^2 r2)).
+struct StageGeom { M33 R; V3 pos, ol, dl, pl, nl; float sx, sy, sxx, sxy, syy, inv_m; };
+
+__device__ __forceinline__ StageGeom stage_geometry(const float* r, V3 o, V3 d, float t) {
+    StageGeom g;
+    g.pos = v3(r[0], r[1], r[2]);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) g.R.m[k] = r[24 + k];
+    SurfRef s;
+    s.c = r[8]; s.k = r[9]; s.kc2 = r[33]; s.n_asph = (int)r[10]; s.asph = r + 11;
+    g.ol = mulT(g.R, o - g.pos); g.dl = mulT(g.R, d);
+    const float x0 = r[6], y0 = r[7];
+    const float x = g.ol.x + t * g.dl.x, y = g.ol.y + t * g.dl.y;
+    const float X = x + x0, Y = y + y0, r2 = X * X + Y * Y;
+    const float ss = 1.0f - s.kc2 * r2;
+    const float inv_s = rsqrtf(ss);
+    float f1 = 0.5f * s.c * inv_s;                                   // f'(r2)
+    float f2 = 0.25f * s.c * s.kc2 * inv_s * inv_s * inv_s;          // f''(r2)
+    if (s.n_asph > 0) {
+        float r4 = r2 * r2, p1 = r2, p0 = 1.0f;                      // r2^(2i+1), r2^(2i)
+        for (int i = 0; i < s.n_asph; ++i) {
+            const float e = (float)(2 * i + 2);
+            f1 += s.asph[i] * e * p1;
+            f2 += s.asph[i] * e * (e - 1.0f) * p0;
+            p1 *= r4; p0 *= r4;
+        }
+    }
+    g.sx = 2.0f * X * f1; g.sy = 2.0f * Y * f1;
+    g.sxx = 2.0f * f1 + 4.0f * X * X * f2; g.sxy = 4.0f * X * Y * f2; g.syy = 2.0f * f1 + 4.0f * Y * Y * f2;
+    g.pl = v3(x, y, sag_fast(s, X, Y) - sag_fast(s, x0, y0));
+    const V3 m = v3(-g.sx, -g.sy, 1.0f);
+    g.inv_m = rsqrtf(dot(m, m));
+    g.nl = g.inv_m * m;
+    return g;
+}
+
+// Reverse pass through one stage.  In: adjoints of the outgoing origin (hit point) g_p, outgoing
+// direction g_r and outgoing value g_vout.  Out: adjoints of the incoming origin/direction/value.
+// t is differentiated implicitly: g(t) = oz + t dz - sag(x, y) = 0 (the fixed point of the Newton scan).
+__device__ __forceinline__ void stage_backward(const StageGeom& g, V3 d, float t, float val_in, V3 g_p, V3 g_r, float g_vout,
+                                               V3& g_o, V3& g_d, float& g_vin) {
+    const V3 nw = mul(g.R, g.nl);
+    const float c = dot(d, nw);
+    // refl = d - 2 c n ; val_out = val_in |c|
+    g_d = g_r;
+    float g_c = -2.0f * dot(g_r, nw) + g_vout * val_in * (c > 0.f ? 1.f : (c < 0.f ? -1.f : 0.f));
+    V3 g_nw = (-2.0f * c) * g_r;
+    g_vin = g_vout * fabsf(c);
+    g_d = g_d + g_c * nw;
+    g_nw = g_nw + g_c * d;
+    // world -> local
+    const V3 g_pl = mulT(g.R, g_p), g_nl = mulT(g.R, g_nw);
+    // n_l = m/|m|, m = (-sx, -sy, 1)
+    const V3 g_m = g.inv_m * (g_nl - dot(g_nl, g.nl) * g.nl);
+    const float g_sx = -g_m.x, g_sy = -g_m.y;
+    // p_l = (x, y, sag(x, y) - z0)
+    float g_x = g_pl.x + g_pl.z * g.sx + g_sx * g.sxx + g_sy * g.sxy;
+    float g_y = g_pl.y + g_pl.z * g.sy + g_sx * g.sxy + g_sy * g.syy;
+    // x = ol.x + t dl.x, y = ol.y + t dl.y
+    V3 g_ol = v3(g_x, g_y, 0.f), g_dl = v3(t * g_x, t * g_y, 0.f);
+    const float g_t = g_x * g.dl.x + g_y * g.dl.y;
+    // implicit: dt = -(dg/d ol . d ol + dg/d dl . d dl) / g',  dg/d ol = (-sx, -sy, 1), dg/d dl = t (-sx, -sy, 1)
+    const float gprime = g.dl.z - (g.sx * g.dl.x + g.sy * g.dl.y);
+    const float k = -g_t / gprime;
+    const V3 q = v3(-g.sx, -g.sy, 1.0f);
+    g_ol = g_ol + k * q;
+    g_dl = g_dl + (k * t) * q;
+    // ol = R^T (o - pos), dl = R^T d
+    g_o = mul(g.R, g_ol);
+    g_d = g_d + mul(g.R, g_dl);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
     v += __shfl_xor_sync(0xffffffffu, v, 16);
     v += __shfl_xor_sync(0xffffffffu, v, 8);
@@ -110,8 +219,8 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-template <int SRC, int SENS>
-__global__ void __launch_bounds__(256, 2)
+template <int SRC, int SENS, bool STAGES>
+__global__ void __launch_bounds__(256, STAGES ? 1 : 2)
 vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float* __restrict__ sources,
            const float* __restrict__ values, const LaunchPlan plan, const FacetLists fl,
            const float* __restrict__ G, const GradsDev gr) {
@@ -121,6 +230,8 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
     stage_obstructions(sc, smem, ob, cull);
     const int n_obs = ob.n_cyl + ob.n_rest;
     float* p = smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri, cull);
+    const float* stage_rec = p;
+    if (STAGES) { stage_mirrors(sc, p); p += stage_floats(sc); }
     const short* lut = nullptr;
     if (SENS == SENS_HEX) {
         short* l = reinterpret_cast<short*>(p);
@@ -182,16 +293,41 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 if (occluded(ob, o, -d, list, n_list_cyl, n_list)) continue;
                 const float c = dot(d, n);
                 const V3 r = d - (2.0f * c) * n;
-                const float val = (sval * (-c)) / w;
-                const float B = dot(r, ns), ndoto = dot(o, ns);
+                const float val0 = (sval * (-c)) / w;
+                // optical stages >= 1: forward with the state the reverse pass needs
+                V3 so[IACT_MAX_STAGES], sd[IACT_MAX_STAGES];
+                float st_t[IACT_MAX_STAGES], sv[IACT_MAX_STAGES];
+                int smi[IACT_MAX_STAGES];
+                V3 oc = o, dc = r;
+                float val = val0;
+                bool alive = true;
+                if (STAGES) {
+                    const float* rec = stage_rec;
+                    for (int k = 0; k < sc.n_stages; ++k) {
+                        so[k] = oc; sd[k] = dc; sv[k] = val;
+                        int mi; float t;
+                        if (!stage_select(sc.stages[k].n, rec, sc.stages[k].verts, oc, dc, mi, t) ||
+                            occluded(ob, oc, dc, nullptr, 0, 0)) { alive = false; break; }
+                        smi[k] = mi; st_t[k] = t;
+                        const StageGeom g = stage_geometry(rec + (size_t)mi * STAGE_REC, oc, dc, t);
+                        const V3 nw = mul(g.R, g.nl);
+                        const float ck = dot(dc, nw);
+                        val *= fabsf(ck);
+                        oc = mul(g.R, g.pl) + g.pos;
+                        dc = dc - (2.0f * ck) * nw;
+                        rec += (size_t)sc.stages[k].n * STAGE_REC;
+                    }
+                }
+                if (!alive) continue;
+                const float B = dot(dc, ns), ndoto = dot(oc, ns);
                 if (fabsf(B) < 1e-10f) continue;
                 const float t = (se.ndotp - ndoto) / B;
                 if (t <= 0.f) continue;
-                const V3 h = o + t * r - ps;
+                const V3 h = oc + t * dc - ps;
                 const float x = dot(h, u1), y = dot(h, u2);
                 float dval, dx, dy;
                 if (!sensor_adjoint<SENS>(se, lut, G, x, y, dval, dx, dy)) continue;
-                // backward
+                // backward: sensor plane
                 const float xb = val * dx, yb = val * dy;           // dL/dx, dL/dy
                 V3 g_o = v3(0.f, 0.f, 0.f), g_r = g_o;
                 if (xb != 0.f || yb != 0.f) {
@@ -199,18 +335,30 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                     g_u1 = g_u1 + xb * h; g_u2 = g_u2 + yb * h;
                     g_ps = g_ps - g_h;
                     g_o = g_h;
-                    const float g_t = dot(g_h, r);
+                    const float g_t = dot(g_h, dc);
                     g_r = t * g_h;
                     const float gA = g_t / B, gB = -g_t * t / B;
-                    g_ns = g_ns + gA * (ps - o) + gB * r;
+                    g_ns = g_ns + gA * (ps - oc) + gB * dc;
                     g_ps = g_ps + gA * ns;
                     g_o = g_o - gA * ns;
                     g_r = g_r + gB * ns;
                 }
+                // backward: stages in reverse order
+                if (STAGES) {
+                    const float* rec = stage_rec;
+                    for (int k = 0; k < sc.n_stages; ++k) rec += (size_t)sc.stages[k].n * STAGE_REC;
+                    for (int k = sc.n_stages - 1; k >= 0; --k) {
+                        rec -= (size_t)sc.stages[k].n * STAGE_REC;
+                        const StageGeom g = stage_geometry(rec + (size_t)smi[k] * STAGE_REC, so[k], sd[k], st_t[k]);
+                        V3 go2, gd2; float gv2;
+                        stage_backward(g, sd[k], st_t[k], sv[k], g_o, g_r, dval, go2, gd2, gv2);
+                        g_o = go2; g_r = gd2; dval = gv2;
+                    }
+                }
                 // val = v (-c)/w
                 float g_c = -dval * sval / w;
                 g_val += dval * (-c) / w;
-                if (gr.weights) atomicAdd(gr.weights + (size_t)f * M + m, -dval * val / w);
+                if (gr.weights) atomicAdd(gr.weights + (size_t)f * M + m, -dval * val0 / w);
                 // r = d - 2 c n ; c = d.n
                 g_c += -2.0f * dot(g_r, n);
                 V3 g_d = g_r + g_c * n;
@@ -311,10 +459,6 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     IACT_REQUIRE(facets && grads && cotangent, "null pointer");
     IACT_REQUIRE(facets->n_facets == d.F && facets->n_samples == d.M, "facet tables do not match the scene");
     IACT_REQUIRE(source_type == IACT_SOURCE_POINT || source_type == IACT_SOURCE_PARALLEL, "bad source_type");
-    if (d.n_stages > 0) {
-        iact_set_error("iact_render_vjp: gradients through optical stages >= 1 are not implemented");
-        return IACT_ERR_UNSUPPORTED;
-    }
     const int S = n_sources;
     if (S <= 0 || d.F == 0 || d.M == 0) return IACT_OK;
     IACT_REQUIRE(sources && values, "null sources/values");
@@ -339,6 +483,7 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     const int threads = 256;
     size_t smem = (size_t)obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, d.cull != 0) * 4 + 16;
     if (hex) smem += (size_t)((d.sens.tq * d.sens.tr + 1) / 2) * 4;
+    smem += (size_t)stage_floats(d) * 4;
     if (d.cull) smem += (size_t)(threads / 32) * ((d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri + 1) & ~1) * 2;
     if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
     auto launch = [&](auto kern) -> int {
@@ -351,8 +496,14 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
         iact_count_launch();
         return iact_check_cuda(cudaGetLastError(), "vjp_kernel launch");
     };
-    if (source_type == IACT_SOURCE_POINT) rc = hex ? launch(vjp_kernel<IACT_SOURCE_POINT, SENS_HEX>) : launch(vjp_kernel<IACT_SOURCE_POINT, SENS_SQUARE>);
-    else rc = hex ? launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_HEX>) : launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_SQUARE>);
+    const bool st2 = d.n_stages > 0;
+    if (source_type == IACT_SOURCE_POINT) {
+        if (hex) rc = st2 ? launch(vjp_kernel<IACT_SOURCE_POINT, SENS_HEX, true>) : launch(vjp_kernel<IACT_SOURCE_POINT, SENS_HEX, false>);
+        else     rc = st2 ? launch(vjp_kernel<IACT_SOURCE_POINT, SENS_SQUARE, true>) : launch(vjp_kernel<IACT_SOURCE_POINT, SENS_SQUARE, false>);
+    } else {
+        if (hex) rc = st2 ? launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_HEX, true>) : launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_HEX, false>);
+        else     rc = st2 ? launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_SQUARE, true>) : launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_SQUARE, false>);
+    }
     if (rc) return rc;
     const float3 se = make_float3(scene->sensor.euler[0], scene->sensor.euler[1], scene->sensor.euler[2]);
     vjp_finalize_kernel<<<(d.F + 127) / 128, 128, 0, st>>>(*facets, gr.facc, gr.sacc, *grads, se);

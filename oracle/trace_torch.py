@@ -83,12 +83,91 @@ def _accumulate(s, x, y, v):
     raise ValueError(t)
 
 
+def _sag_t(x, y, c, k, asph):
+    r2 = x * x + y * y
+    z = r2 * c / (1 + torch.sqrt(1 - (1 + k) * c * c * r2))
+    for i, a in enumerate(np.asarray(asph, np.float64).tolist()):
+        z = z + a * r2 ** (2 * i + 2)
+    return z
+
+
+def _dsag_t(x, y, c, k, asph):
+    r2 = x * x + y * y
+    f1 = 0.5 * c / torch.sqrt(1 - (1 + k) * c * c * r2)
+    for i, a in enumerate(np.asarray(asph, np.float64).tolist()):
+        f1 = f1 + a * (2 * i + 2) * r2 ** (2 * i + 1)
+    return 2 * x * f1, 2 * y * f1
+
+
+def _reflect_at_stage(o, d, val, stage_groups, obstructions):
+    """render.py:44-115 for one optical stage >= 1, differentiable in (o, d, val).
+    The mirror choice, the hit mask and the shadow mask come from the NumPy oracle (constants); the
+    ray parameter is the NumPy oracle's converged Newton root refined by one differentiable Newton
+    step, whose derivative is the implicit-function derivative that autodiff of the reference's
+    10-step scan converges to."""
+    on, dn = o.detach().numpy(), d.detach().numpy()
+    best_t = np.full(on.shape[:-1], np.inf)
+    best_key = np.full(on.shape[:-1], -1)
+    cands = []
+    for g in stage_groups:
+        for mi in range(g["positions"].shape[0]):
+            pos = g["positions"][mi].astype(np.float64)
+            R = otrace.euler_to_matrix(g["rotations"][mi], np.float64)
+            with np.errstate(all="ignore"):
+                ol = np.einsum("ij,...j->...i", R.T, on - pos)
+                dl = np.einsum("ij,...j->...i", R.T, dn)
+                ts, pl, _ = otrace.surface_intersect(ol, dl, g["offsets"][mi], g["curvature"], g["conic"], g["aspheric"], np.float64)
+                ok = otrace.check_aperture(g, pl[..., 0], pl[..., 1], mi, np.float64)
+            ts = np.where(ok, ts, np.inf)
+            closer = ts < best_t
+            best_t = np.where(closer, ts, best_t)
+            best_key = np.where(closer, len(cands), best_key)
+            cands.append((g, mi))
+    hit = best_t < 1e10
+    shadow = otrace.check_occlusions(on, dn, obstructions, np.float64)
+    p_out = torch.zeros_like(o)
+    n_out = torch.zeros_like(o)
+    for key, (g, mi) in enumerate(cands):
+        m = torch.from_numpy((best_key == key) & hit)
+        if not m.any():
+            continue
+        c, k, asph = g["curvature"], g["conic"], g["aspheric"]
+        pos = torch.tensor(g["positions"][mi].astype(np.float64))
+        R = euler_to_matrix(torch.tensor(g["rotations"][mi].astype(np.float64)))
+        x0, y0 = float(g["offsets"][mi][0]), float(g["offsets"][mi][1])
+        z0 = _sag_t(torch.tensor(x0, dtype=DT), torch.tensor(y0, dtype=DT), c, k, asph)
+        ol = (o - pos) @ R          # R^T (o - pos)
+        dl = d @ R
+        t0 = torch.from_numpy(np.where(np.isfinite(best_t), best_t, 1.0))
+        x, y = ol[..., 0] + t0 * dl[..., 0], ol[..., 1] + t0 * dl[..., 1]
+        gval = (ol[..., 2] + t0 * dl[..., 2]) - (_sag_t(x + x0, y + y0, c, k, asph) - z0)
+        sx, sy = _dsag_t(x + x0, y + y0, c, k, asph)
+        t = t0 - gval / (dl[..., 2] - (sx * dl[..., 0] + sy * dl[..., 1]))
+        x, y = ol[..., 0] + t * dl[..., 0], ol[..., 1] + t * dl[..., 1]
+        pl = torch.stack([x, y, _sag_t(x + x0, y + y0, c, k, asph) - z0], -1)
+        sx, sy = _dsag_t(x + x0, y + y0, c, k, asph)
+        nl = torch.stack([-sx, -sy, torch.ones_like(sx)], -1)
+        nl = nl / nl.norm(dim=-1, keepdim=True)
+        pw = pl @ R.T + pos
+        nw = nl @ R.T
+        p_out = torch.where(m[..., None], pw, p_out)
+        n_out = torch.where(m[..., None], nw, n_out)
+    cos = (d * n_out).sum(-1)
+    refl = d - 2 * cos[..., None] * n_out
+    new_val = val * torch.from_numpy(hit.astype(np.float64)) * torch.from_numpy(shadow) * cos.abs()
+    return p_out, refl, new_val
+
+
 def render(scene, leaves, sources, values, source_type="point", sensor_idx=0):
     """Differentiable render.  ``leaves`` = dict of float64 torch tensors (may require grad):
     positions (F,3), rotations (F,3), scale (F,), weights (F,M,1), sensor_position (3,), sensor_rotation (3,);
-    ``sources`` (S,3) and ``values`` (S,) float64 torch tensors.  Single stage-0 group only."""
+    ``sources`` (S,3) and ``values`` (S,) float64 torch tensors.  One stage-0 group; groups of later
+    optical stages are traversed with ``_reflect_at_stage``."""
     g = scene["groups"][0]
-    assert all(gr["stage"] == 0 for gr in scene["groups"]) and len(scene["groups"]) == 1
+    assert g["stage"] == 0 and all(gr["stage"] > 0 for gr in scene["groups"][1:]), "one stage-0 group, then later stages"
+    later = {}
+    for gr in scene["groups"][1:]:
+        later.setdefault(gr["stage"], []).append(gr)
     s = scene["sensors"][sensor_idx]
     pts = torch.from_numpy(g["points"].astype(np.float64))
     nrm = torch.from_numpy(g["normals"].astype(np.float64))
@@ -120,9 +199,12 @@ def render(scene, leaves, sources, values, source_type="point", sensor_idx=0):
         c = (d * n[None]).sum(-1)
         r = d - 2 * c[..., None] * n[None]
         val = values[:, None] * (-c) / leaves["weights"][f][None, :, 0] * shadow
+        o_cur = p[None].expand_as(r)
+        for stage in sorted(later):
+            o_cur, r, val = _reflect_at_stage(o_cur, r, val, later[stage], scene["obstructions"])
         ndotd = (r * ns).sum(-1)
-        t = ((ns * ps).sum() - (p * ns).sum(-1)[None]) / ndotd
-        h = p[None] + t[..., None] * r - ps
+        t = ((ns * ps).sum() - (o_cur * ns).sum(-1)) / ndotd
+        h = o_cur + t[..., None] * r - ps
         x, y = (h * u1).sum(-1), (h * u2).sum(-1)
         ok = (t > 0) & (ndotd.abs() >= 1e-10)
         x = torch.where(ok, x, torch.full_like(x, 1e10))
