@@ -163,6 +163,12 @@ def _inputs(sources, values):
     return src, val, dev
 
 
+def _out(t):
+    if isinstance(t, tuple):
+        return tuple(_out(x) for x in t)
+    return t.cpu().numpy() if config.return_numpy else t
+
+
 def _stype(source_type) -> int:
     # any string other than 'point' is treated as parallel (render.py:129-133)
     return N.SOURCE_POINT if source_type == "point" else N.SOURCE_PARALLEL
@@ -178,10 +184,10 @@ def render(tel, sources, values, source_type="point", sensor_idx: int = 0) -> to
     sc, sensor = build_scene(tel, sensor_idx, keep)
     out = torch.empty(sensor.get_accumulator_shape(), dtype=torch.float32, device=dev)
     if sc is None:
-        return out.zero_()
+        return _out(out.zero_())
     N.check(N.lib().iact_render(sc, N.ptr(src), N.ptr(val), src.shape[0], _stype(source_type), N.ptr(out),
                                 N.stream_ptr()), "render")
-    return out
+    return _out(out)
 
 
 def render_debug(tel, sources, values, source_type="point", sensor_idx: int = 0, return_pixels: bool = False):
@@ -200,7 +206,7 @@ def render_debug(tel, sources, values, source_type="point", sensor_idx: int = 0,
     pix = torch.empty((n,), dtype=torch.int32, device=dev) if return_pixels else None
     N.check(N.lib().iact_render_debug(sc, N.ptr(src), N.ptr(val), src.shape[0], _stype(source_type), N.ptr(xy),
                                       N.ptr(v), N.ptr(pix), N.stream_ptr()), "render_debug")
-    return (xy, v, pix) if return_pixels else (xy, v)
+    return _out((xy, v, pix) if return_pixels else (xy, v))
 
 
 def render_response_matrix(tel, sources, values, source_type="point", sensor_idx: int = 0) -> torch.Tensor:
@@ -211,7 +217,7 @@ def render_response_matrix(tel, sources, values, source_type="point", sensor_idx
     npix = math.prod(sensor.get_accumulator_shape())
     out = torch.empty((src.shape[0], npix), dtype=torch.float32, device=dev)
     if sc is None:
-        return out.zero_()
+        return _out(out.zero_())
     N.check(N.lib().iact_response_matrix(sc, N.ptr(src), N.ptr(val), src.shape[0], _stype(source_type), N.ptr(out),
                                          N.stream_ptr()), "render_response_matrix")
-    return out
+    return _out(out)

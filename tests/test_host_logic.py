@@ -179,3 +179,30 @@ def test_product_never_imports_oracle():
         assert not re.search(r"^\s*(from|import)\s+oracle\b", p.read_text(), re.M), p
     for p in list(root.rglob("*.cu")) + list(root.rglob("*.cuh")):
         assert "oracle" not in p.read_text().lower(), p
+
+
+def test_public_intersection_functions_match_reference_goldens():
+    """iactrace_b200.core.intersect_* (torch API mirrors) against vectors from the executed reference."""
+    from iactrace_b200 import core as C
+    G = np.load(Path(__file__).parent / "golden" / "reference_golden.npz")
+    o, d = torch.tensor(G["unit/o"]), torch.tensor(G["unit/d"])
+    f = lambda *a: torch.tensor(a, dtype=torch.float32)
+
+    def cmp(t, key):
+        t, g = t.cpu().numpy(), G[key]
+        assert np.array_equal(np.isfinite(t), np.isfinite(g)), key
+        m = np.isfinite(g)
+        np.testing.assert_allclose(t[m], g[m], rtol=2e-5, err_msg=key)
+
+    cmp(C.intersect_cylinder(o, d, f(-1, 0.5, 2), f(2, -0.5, 4), 0.8), "unit/cylinder")
+    cmp(C.intersect_box(o, d, f(-1, -2, 1), f(1.5, 0.5, 3)), "unit/box")
+    cmp(C.intersect_sphere(o, d, f(0.5, 0.5, 3), 1.7), "unit/sphere")
+    th = np.deg2rad(30.0)
+    Rz = torch.tensor([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], dtype=torch.float32)
+    cmp(C.intersect_oriented_box(o, d, f(0.5, 0, 3), f(1.5, 0.6, 1.0), Rz), "unit/obox")
+    cmp(C.intersect_triangle(o, d, f(-4, -4, 3), f(4, -3, 3.5), f(0, 4, 2.5)), "unit/triangle")
+    cmp(C.intersect_conic(torch.tensor(G["unit/surf_o"]), torch.tensor(G["unit/surf_d"]), 0.05, -1.0), "unit/conic_t")
+    p = C.intersect_plane(o, d, f(0.1, -0.2, 5), C.euler_to_matrix([3.0, -2.0, 20.0])).cpu().numpy()
+    g = G["unit/plane"]
+    assert np.array_equal(p[:, 0] > 1e9, g[:, 0] > 1e9)
+    np.testing.assert_allclose(p[g[:, 0] < 1e9], g[g[:, 0] < 1e9], rtol=1e-4, atol=1e-5)
