@@ -86,7 +86,7 @@ def test_functional_edits_reach_the_kernels():
     assert abs(got.sum() - want.sum()) < 2e-3 * want.sum()
     assert abs(got.sum() - float(base.sum())) > 1e-3 or np.abs(got - base.cpu().numpy()).max() > 0
     # the original is untouched (cache keyed per Telescope)
-    torch.testing.assert_close(render(tel, src, val, "point", 1), base, rtol=0, atol=0)
+    torch.testing.assert_close(render(tel, src, val, "point", 1), base, rtol=2e-6, atol=0)   # atomic order varies
     # removing obstructions only adds light
     assert float(render(tel.clear_obstructions(), src, val, "point", 1).sum()) > float(base.sum())
 
