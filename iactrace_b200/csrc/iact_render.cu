@@ -88,6 +88,37 @@ __device__ __forceinline__ void warp_hist_add(float* hist, int pix, float val) {
     }
 }
 
+// Per-warp-item pixel cache: the rays of one (facet, source) pair land in 1-3 hex pixels, so the warp
+// keeps up to three (pixel, per-lane partial sum) slots in registers across all its iterations and
+// touches the shared histogram once per slot at the end of the item; rays outside the three cached
+// pixels fall back to a direct shared atomic.  Slot pixels are warp-uniform.
+struct PixCache {
+    int p0, p1, p2;
+    float a0, a1, a2;
+    __device__ __forceinline__ void reset() { p0 = p1 = p2 = -1; a0 = a1 = a2 = 0.f; }
+    // must be called by all 32 lanes; pix < 0 = nothing to add
+    __device__ __forceinline__ void add(float* hist, int pix, float val) {
+        bool matched = (pix < 0) | (pix == p0) | (pix == p1) | (pix == p2);
+        unsigned un = __ballot_sync(0xffffffffu, !matched);
+        while (un != 0u && p2 < 0) {                        // a free slot and an unmatched pixel
+            const int lp = __shfl_sync(0xffffffffu, pix, __ffs(un) - 1);
+            if (p0 < 0) p0 = lp; else if (p1 < 0) p1 = lp; else p2 = lp;
+            matched = matched | (pix == lp);
+            un = __ballot_sync(0xffffffffu, !matched);
+        }
+        if (pix == p0) a0 += val;
+        else if (pix == p1) a1 += val;
+        else if (pix == p2) a2 += val;
+        else if (pix >= 0) atomicAdd(hist + pix, val);
+    }
+    __device__ __forceinline__ void flush(float* hist) {
+        const unsigned lane = threadIdx.x & 31u;
+        if (p0 >= 0) { float v = a0; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); if (lane == 0 && v != 0.f) atomicAdd(hist + p0, v); }
+        if (p1 >= 0) { float v = a1; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); if (lane == 0 && v != 0.f) atomicAdd(hist + p1, v); }
+        if (p2 >= 0) { float v = a2; for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); if (lane == 0 && v != 0.f) atomicAdd(hist + p2, v); }
+    }
+};
+
 // ---------------------------------------------------------------- the kernel
 #ifndef IACT_MIN_BLOCKS
 #define IACT_MIN_BLOCKS 4
@@ -144,6 +175,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 else            n_list = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, n_list_cyl);
             }
             const float4* tab = sc.world + ((size_t)f * M) * 2;
+            PixCache cache;
+            cache.reset();
             for (int mb = m0; mb < m1; mb += 32) {
                 const int m = mb + lane;
                 const bool live = m < m1;
@@ -189,13 +222,14 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                     const bool add = live && val != 0.f;
                     if (SENS == SENS_HEX) {
                         if (soft) { if (add) splat_soft_hex(sc.sens, lut, x, y, val, hist); }
-                        else warp_hist_add(hist, add ? hex_pixel(sc.sens, lut, x, y) : -1, val);
+                        else cache.add(hist, add ? hex_pixel(sc.sens, lut, x, y) : -1, val);
                     } else if (add) {
                         if (soft) splat_soft_square(sc.sens, x, y, val, gout);
                         else { const int pix = square_pixel(sc.sens, x, y); if (pix >= 0) atomicAdd(gout + pix, val); }
                     }
                 }
             }
+            if (SENS == SENS_HEX && MODE != MODE_DEBUG && !soft) cache.flush(hist);
             __syncwarp();
         }
         if (MODE == MODE_MATRIX && SENS == SENS_HEX) {
