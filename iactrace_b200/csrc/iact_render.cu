@@ -106,10 +106,12 @@ struct PixCache {
             matched = matched | (pix == lp);
             un = __ballot_sync(0xffffffffu, !matched);
         }
-        if (pix == p0) a0 += val;
-        else if (pix == p1) a1 += val;
-        else if (pix == p2) a2 += val;
-        else if (pix >= 0) atomicAdd(hist + pix, val);
+        if (pix >= 0) {                                     // empty slots hold -1: never match them
+            if (pix == p0) a0 += val;
+            else if (pix == p1) a1 += val;
+            else if (pix == p2) a2 += val;
+            else atomicAdd(hist + pix, val);
+        }
     }
     __device__ __forceinline__ void flush(float* hist) {
         const unsigned lane = threadIdx.x & 31u;
