@@ -104,5 +104,5 @@ def test_numpy_output_option():
     finally:
         config.return_numpy = False
     assert isinstance(img, np.ndarray) and isinstance(pts, np.ndarray) and isinstance(mat, np.ndarray)
-    np.testing.assert_array_equal(img, ref)
+    np.testing.assert_allclose(img, ref, rtol=1e-6)          # atomic order varies run to run
     assert mat.shape == (1, 960) and pts.shape == (3 * 8, 2) and vals.shape == (24,)
