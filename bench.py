@@ -323,7 +323,7 @@ def main():
         achieved = rays_per_step * f_culled / kern_s / 1e12
         out_bytes = (out.numel() * 4) + h2d  # algorithmic HBM bytes per launch: image + sources (tables are L2-resident)
         roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                    "traffic": None,
+                    "traffic": _traffic(args.workload),
                     "peak_source": "measured live: iact_probe_fp32 (dependent-free FFMA chains, all SMs); MEASURED_PEAKS.json has no FP32 CUDA-core figure",
                     "flops_per_ray": {"after_exact_culling": f_culled, "brute_force_reference": f_brute,
                                       "mean_cylinders_tested": n_cyl_kept / max(n_pairs, 1),
@@ -351,6 +351,14 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (null if not captured)."""
+    try:
+        return json.loads((ROOT / "profiles" / "traffic.json").read_text())[workload]["bytes"]
+    except Exception:
+        return None
 
 
 def _hbm_peak():
