@@ -46,6 +46,9 @@ WORKLOADS = {
     "ct5_point_4096x4096_hex": dict(scene="CT5", M=4096, grid=("point", 64, 1.5), sensor=0, mode="render"),
     "ct3_matrix_64x64_M64": dict(scene="CT3", M=64, grid=("parallel", 64, 5.5), sensor=0, mode="matrix", roughness=24, seed=42),
     "ct3_matrix_64x64_M1000": dict(scene="CT3", M=1000, grid=("parallel", 64, 5.5), sensor=0, mode="matrix", roughness=24, seed=42),
+    # examples/ResponseMatrix.ipynb cell 11 at full size: 512x512 directions x 380 facets x 64 samples = 6.4e9 rays,
+    # output 262144 x 960 f32 = 1.0 GB (the notebook reports 30.3 s wall on unstated hardware)
+    "ct3_matrix_512x512_M64": dict(scene="CT3", M=64, grid=("parallel", 512, 5.5), sensor=0, mode="matrix", roughness=24, seed=42),
     # BASELINE config 3: Cassegrain (examples/Cassegrain.ipynb cell 3) + synthetic obstructions, 1e9 rays
     "cassegrain_1e9": dict(scene="cassegrain", M=16667, grid=("stars", 10000, 3.0), sensor=0, mode="render"),
 }
