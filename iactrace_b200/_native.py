@@ -64,7 +64,8 @@ class IactFacets(C.Structure):
 
 class IactGrads(C.Structure):
     _fields_ = [("positions", _fp), ("rotations", _fp), ("scale", _fp), ("weights", _fp), ("values", _fp),
-                ("sources", _fp), ("sensor_position", _fp), ("sensor_euler", _fp)]
+                ("sources", _fp), ("sensor_position", _fp), ("sensor_euler", _fp),
+                ("stage_positions", _fp), ("stage_rotations", _fp)]
 
 
 _KEY = C.c_uint32 * 2

@@ -16,6 +16,10 @@ def _leaves(tel, sensor_idx):
         out += [g.positions, g.rotations, g.perturbation_scale, g.weights]
     s = tel.sensors[sensor_idx]
     out += [s.position, s.rotation]
+    for k in stages:                       # stage >= 1 mirror poses, in the flat order of IactScene.stages
+        if k != 0:
+            for g in stages[k]:
+                out += [g.positions, g.rotations]
     return out
 
 
@@ -32,7 +36,6 @@ class _Render(torch.autograd.Function):
         from .render import build_scene, _stype
         ctx.tel, ctx.source_type, ctx.sensor_idx = tel, source_type, sensor_idx
         ctx.save_for_backward(src, val)
-        ctx.n_groups = (len(leaves) - 2) // 4
         with torch.no_grad():
             keep = []
             sc, sensor = build_scene(tel, sensor_idx, keep)
@@ -55,6 +58,10 @@ class _Render(torch.autograd.Function):
         g_val = torch.zeros_like(val)
         g_spos = torch.zeros(3, device=dev)
         g_srot = torch.zeros(3, device=dev)
+        later = [g for k in stages if k != 0 for g in stages[k]]
+        n2 = sum(len(g) for g in later)
+        g_mpos = torch.zeros((n2, 3), device=dev) if n2 else None
+        g_mrot = torch.zeros((n2, 3), device=dev) if n2 else None
         grads = []
         keep = []
         sc, _ = build_scene(tel, sensor_idx, keep)
@@ -71,13 +78,17 @@ class _Render(torch.autograd.Function):
                 sub.world = sc.world + off * M * 8 * 4
                 sub.bounds = sc.bounds + off * 4 * 4
                 gr_struct = N.IactGrads(N.ptr(gp), N.ptr(gr), N.ptr(gs), N.ptr(gw), N.ptr(g_val), N.ptr(g_src),
-                                        N.ptr(g_spos), N.ptr(g_srot))
+                                        N.ptr(g_spos), N.ptr(g_srot), N.ptr(g_mpos), N.ptr(g_mrot))
                 N.check(N.lib().iact_render_vjp(sub, fa, N.ptr(src), N.ptr(val), src.shape[0],
                                                 _stype(ctx.source_type), N.ptr(g_img), gr_struct, N.stream_ptr()),
                         "render_vjp")
             grads += [gp, gr, gs, gw]
             off += F
-        return (None, None, None, g_src, g_val, *grads, g_spos, g_srot)
+        stage_grads, off2 = [], 0
+        for g in later:
+            stage_grads += [g_mpos[off2:off2 + len(g)], g_mrot[off2:off2 + len(g)]]
+            off2 += len(g)
+        return (None, None, None, g_src, g_val, *grads, g_spos, g_srot, *stage_grads)
 
 
 def render_with_grad(tel, sources, values, source_type, sensor_idx):

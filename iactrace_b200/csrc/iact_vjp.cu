@@ -19,6 +19,7 @@ struct GradsDev {
     float *weights, *values, *sources;
     float* facc;   // (F,13): dL/dR row-major (9), dL/dpos (3), dL/dscale (1)
     float* sacc;   // 12: dL/d sensor pos (3), dL/d sensor R (9: u1,u2,n as columns -> row-major R)
+    float* macc;   // (N2,12) or null: per stage>=1 mirror dL/dR row-major (9), dL/dpos (3)
 };
 
 // d(image . G)/d(val) and /d(x, y) for one hit.  Returns false if the hit contributes nothing.
@@ -177,8 +178,8 @@ __device__ __forceinline__ StageGeom stage_geometry(const float* r, V3 o, V3 d, 
 // Reverse pass through one stage.  In: adjoints of the outgoing origin (hit point) g_p, outgoing
 // direction g_r and outgoing value g_vout.  Out: adjoints of the incoming origin/direction/value.
 // t is differentiated implicitly: g(t) = oz + t dz - sag(x, y) = 0 (the fixed point of the Newton scan).
-__device__ __forceinline__ void stage_backward(const StageGeom& g, V3 d, float t, float val_in, V3 g_p, V3 g_r, float g_vout,
-                                               V3& g_o, V3& g_d, float& g_vin) {
+__device__ __forceinline__ void stage_backward(const StageGeom& g, V3 o, V3 d, float t, float val_in, V3 g_p, V3 g_r, float g_vout,
+                                               V3& g_o, V3& g_d, float& g_vin, float* macc) {
     const V3 nw = mul(g.R, g.nl);
     const float c = dot(d, nw);
     // refl = d - 2 c n ; val_out = val_in |c|
@@ -208,6 +209,19 @@ __device__ __forceinline__ void stage_backward(const StageGeom& g, V3 d, float t
     // ol = R^T (o - pos), dl = R^T d
     g_o = mul(g.R, g_ol);
     g_d = g_d + mul(g.R, g_dl);
+    if (macc) {
+        // mirror pose adjoints: pw = R pl + pos, nw = R nl, ol = R^T (o - pos), dl = R^T d
+        const V3 oc = o - g.pos;
+        const float a[3] = {g_p.x, g_p.y, g_p.z}, b[3] = {g_nw.x, g_nw.y, g_nw.z};
+        const float pl[3] = {g.pl.x, g.pl.y, g.pl.z}, nl[3] = {g.nl.x, g.nl.y, g.nl.z};
+        const float oc3[3] = {oc.x, oc.y, oc.z}, d3[3] = {d.x, d.y, d.z};
+        const float gol[3] = {g_ol.x, g_ol.y, g_ol.z}, gdl[3] = {g_dl.x, g_dl.y, g_dl.z};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) macc[3 * i + j] += a[i] * pl[j] + b[i] * nl[j] + oc3[i] * gol[j] + d3[i] * gdl[j];
+        macc[9] += g_p.x - g_o.x; macc[10] += g_p.y - g_o.y; macc[11] += g_p.z - g_o.z;
+    }
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -276,6 +290,10 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
             float gR[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             V3 g_pos = v3(0.f, 0.f, 0.f);
             float g_scale = 0.f;
+            // stage >= 1 mirror adjoints: one register set per lane for the first stage's mirror 0..; rays
+            // that use another (stage, mirror) fall back to direct atomics
+            float mreg[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            int mreg_id = -1;                                      // flat mirror id the register set belongs to
 
             for (int m = m0 + lane; m < m1; m += 32) {
                 const size_t li = ((size_t)f * M + m) * 3;
@@ -351,7 +369,20 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                         rec -= (size_t)sc.stages[k].n * STAGE_REC;
                         const StageGeom g = stage_geometry(rec + (size_t)smi[k] * STAGE_REC, so[k], sd[k], st_t[k]);
                         V3 go2, gd2; float gv2;
-                        stage_backward(g, sd[k], st_t[k], sv[k], g_o, g_r, dval, go2, gd2, gv2);
+                        if (STAGES && gr.macc) {
+                            int flat = smi[k];
+                            for (int q = 0; q < k; ++q) flat += sc.stages[q].n;
+                            if (mreg_id < 0) mreg_id = flat;
+                            if (flat == mreg_id) {
+                                stage_backward(g, so[k], sd[k], st_t[k], sv[k], g_o, g_r, dval, go2, gd2, gv2, mreg);
+                            } else {
+                                float tmp[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                stage_backward(g, so[k], sd[k], st_t[k], sv[k], g_o, g_r, dval, go2, gd2, gv2, tmp);
+                                for (int q = 0; q < 12; ++q) if (tmp[q] != 0.f) atomicAdd(gr.macc + (size_t)flat * 12 + q, tmp[q]);
+                            }
+                        } else {
+                            stage_backward(g, so[k], sd[k], st_t[k], sv[k], g_o, g_r, dval, go2, gd2, gv2, nullptr);
+                        }
                         g_o = go2; g_r = gd2; dval = gv2;
                     }
                 }
@@ -388,6 +419,17 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
             { const float v = warp_sum(g_pos.y); if (lane == 0 && v != 0.f) atomicAdd(acc + 10, v); }
             { const float v = warp_sum(g_pos.z); if (lane == 0 && v != 0.f) atomicAdd(acc + 11, v); }
             { const float v = warp_sum(g_scale); if (lane == 0 && v != 0.f) atomicAdd(acc + 12, v); }
+            if (STAGES && gr.macc) {
+                // lanes may have cached different mirrors: reduce per distinct id
+                unsigned todo = __ballot_sync(0xffffffffu, mreg_id >= 0);
+                while (todo) {
+                    const int id = __shfl_sync(0xffffffffu, mreg_id, __ffs(todo) - 1);
+                    const bool mine = mreg_id == id;
+#pragma unroll
+                    for (int q = 0; q < 12; ++q) { const float v = warp_sum(mine ? mreg[q] : 0.f); if (lane == 0 && v != 0.f) atomicAdd(gr.macc + (size_t)id * 12 + q, v); }
+                    todo &= ~__ballot_sync(0xffffffffu, mine);
+                }
+            }
             __syncwarp();
         }
         // per-source adjoints
@@ -426,9 +468,25 @@ __device__ __forceinline__ void euler_adjoint(float tip, float tilt, float rot, 
     mm(Ry, Rx, T);  mm(dRz, T, U); out3[2] = inner(gR, U) * D2R;
 }
 
+struct StageList { int n_stages; StageDev st[IACT_MAX_STAGES]; };
+
 __global__ void vjp_finalize_kernel(IactFacets fa, const float* __restrict__ facc, const float* __restrict__ sacc,
-                                    IactGrads out, float3 sensor_euler) {
+                                    const float* __restrict__ macc, StageList sl, IactGrads out, float3 sensor_euler) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (macc && f == 0) {
+        int flat = 0;
+        for (int k = 0; k < sl.n_stages; ++k)
+            for (int i = 0; i < sl.st[k].n; ++i, ++flat) {
+                const float* r = sl.st[k].rec + (size_t)i * IACT_MIRROR_REC;
+                const float* a = macc + (size_t)flat * 12;
+                if (out.stage_rotations) {
+                    float e[3];
+                    euler_adjoint(r[3], r[4], r[5], a, e);
+                    for (int q = 0; q < 3; ++q) out.stage_rotations[3 * flat + q] += e[q];
+                }
+                if (out.stage_positions) for (int q = 0; q < 3; ++q) out.stage_positions[3 * flat + q] += a[9 + q];
+            }
+    }
     if (f < fa.n_facets) {
         const float* a = facc + (size_t)f * 13;
         if (out.rotations) {
@@ -471,7 +529,10 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     FacetLists fl;
     fl.ids = nullptr; fl.count = nullptr; fl.stride = 0;
     if (d.cull && S >= 4) { rc = run_facet_cull(d, sources, S, source_type, cull_scr, fl, st); if (rc) return rc; }
-    const size_t acc_floats = (size_t)d.F * 13 + 12;
+    int n2 = 0;
+    for (int k = 0; k < d.n_stages; ++k) n2 += d.stages[k].n;
+    const bool want_stage = n2 > 0 && (grads->stage_positions || grads->stage_rotations);
+    const size_t acc_floats = (size_t)d.F * 13 + 12 + (want_stage ? (size_t)n2 * 12 : 0);
     rc = acc_scr.alloc(acc_floats * sizeof(float), st);
     if (rc) return rc;
     IACT_CUDA(cudaMemsetAsync(acc_scr.ptr, 0, acc_floats * sizeof(float), st));
@@ -479,6 +540,7 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     gr.weights = grads->weights; gr.values = grads->values; gr.sources = grads->sources;
     gr.facc = reinterpret_cast<float*>(acc_scr.ptr);
     gr.sacc = gr.facc + (size_t)d.F * 13;
+    gr.macc = want_stage ? gr.sacc + 12 : nullptr;
 
     const int threads = 256;
     size_t smem = (size_t)obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, d.cull != 0) * 4 + 16;
@@ -506,7 +568,10 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     }
     if (rc) return rc;
     const float3 se = make_float3(scene->sensor.euler[0], scene->sensor.euler[1], scene->sensor.euler[2]);
-    vjp_finalize_kernel<<<(d.F + 127) / 128, 128, 0, st>>>(*facets, gr.facc, gr.sacc, *grads, se);
+    StageList sl;
+    sl.n_stages = d.n_stages;
+    for (int k = 0; k < IACT_MAX_STAGES; ++k) sl.st[k] = d.stages[k];
+    vjp_finalize_kernel<<<(d.F + 127) / 128, 128, 0, st>>>(*facets, gr.facc, gr.sacc, gr.macc, sl, *grads, se);
     iact_count_launch();
     return iact_check_cuda(cudaGetLastError(), "vjp_finalize_kernel launch");
 }

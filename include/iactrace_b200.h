@@ -133,6 +133,8 @@ typedef struct IactGrads {
     float* sources;        /* device (S,3) */
     float* sensor_position;/* device (3,)  */
     float* sensor_euler;   /* device (3,)  */
+    float* stage_positions;/* device (N2,3): mirrors of optical stages >= 1, flat in IactScene.stages order */
+    float* stage_rotations;/* device (N2,3): Euler degrees                                                  */
 } IactGrads;
 
 const char* iact_last_error(void);

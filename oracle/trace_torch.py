@@ -99,7 +99,7 @@ def _dsag_t(x, y, c, k, asph):
     return 2 * x * f1, 2 * y * f1
 
 
-def _reflect_at_stage(o, d, val, stage_groups, obstructions):
+def _reflect_at_stage(o, d, val, stage_groups, obstructions, stage_leaves=None):
     """render.py:44-115 for one optical stage >= 1, differentiable in (o, d, val).
     The mirror choice, the hit mask and the shadow mask come from the NumPy oracle (constants); the
     ray parameter is the NumPy oracle's converged Newton root refined by one differentiable Newton
@@ -132,8 +132,9 @@ def _reflect_at_stage(o, d, val, stage_groups, obstructions):
         if not m.any():
             continue
         c, k, asph = g["curvature"], g["conic"], g["aspheric"]
-        pos = torch.tensor(g["positions"][mi].astype(np.float64))
-        R = euler_to_matrix(torch.tensor(g["rotations"][mi].astype(np.float64)))
+        lv = stage_leaves.get(id(g)) if stage_leaves else None
+        pos = lv["positions"][mi] if lv else torch.tensor(g["positions"][mi].astype(np.float64))
+        R = euler_to_matrix(lv["rotations"][mi] if lv else torch.tensor(g["rotations"][mi].astype(np.float64)))
         x0, y0 = float(g["offsets"][mi][0]), float(g["offsets"][mi][1])
         z0 = _sag_t(torch.tensor(x0, dtype=DT), torch.tensor(y0, dtype=DT), c, k, asph)
         ol = (o - pos) @ R          # R^T (o - pos)
@@ -166,8 +167,11 @@ def render(scene, leaves, sources, values, source_type="point", sensor_idx=0):
     g = scene["groups"][0]
     assert g["stage"] == 0 and all(gr["stage"] > 0 for gr in scene["groups"][1:]), "one stage-0 group, then later stages"
     later = {}
-    for gr in scene["groups"][1:]:
+    stage_leaves = {}
+    for i, gr in enumerate(scene["groups"][1:]):
         later.setdefault(gr["stage"], []).append(gr)
+        if leaves.get("stage"):
+            stage_leaves[id(gr)] = leaves["stage"][i]     # {"positions": (N,3), "rotations": (N,3)} torch leaves
     s = scene["sensors"][sensor_idx]
     pts = torch.from_numpy(g["points"].astype(np.float64))
     nrm = torch.from_numpy(g["normals"].astype(np.float64))
@@ -201,7 +205,7 @@ def render(scene, leaves, sources, values, source_type="point", sensor_idx=0):
         val = values[:, None] * (-c) / leaves["weights"][f][None, :, 0] * shadow
         o_cur = p[None].expand_as(r)
         for stage in sorted(later):
-            o_cur, r, val = _reflect_at_stage(o_cur, r, val, later[stage], scene["obstructions"])
+            o_cur, r, val = _reflect_at_stage(o_cur, r, val, later[stage], scene["obstructions"], stage_leaves)
         ndotd = (r * ns).sum(-1)
         t = ((ns * ps).sum() - (o_cur * ns).sum(-1)) / ndotd
         h = o_cur + t[..., None] * r - ps

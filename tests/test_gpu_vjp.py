@@ -44,7 +44,12 @@ def _grads_cuda(tel, src, val, stype, G):
     g2 = replace(g, positions=leaf["positions"], rotations=leaf["rotations"], perturbation_scale=leaf["scale"],
                  weights=leaf["weights"])
     s2 = replace(tel.sensors[0], position=leaf["sensor_position"], rotation=leaf["sensor_rotation"])
-    tel2 = replace(tel, mirror_groups=[g2] + list(tel.mirror_groups[1:]), sensors=[s2] + tel.sensors[1:])
+    later = []
+    for i, gl in enumerate(tel.mirror_groups[1:]):
+        leaf[f"stage{i}_positions"] = gl.positions.detach().clone().requires_grad_(True)
+        leaf[f"stage{i}_rotations"] = gl.rotations.detach().clone().requires_grad_(True)
+        later.append(replace(gl, positions=leaf[f"stage{i}_positions"], rotations=leaf[f"stage{i}_rotations"]))
+    tel2 = replace(tel, mirror_groups=[g2] + later, sensors=[s2] + tel.sensors[1:])
     img = render(tel2, leaf["sources"], leaf["values"], stype, 0)
     assert img.requires_grad
     (img * torch.tensor(G, device="cuda", dtype=torch.float32).reshape(img.shape)).sum().backward()
@@ -57,12 +62,16 @@ def _grads_oracle(tel, src, val, stype, G):
     T = lambda a: torch.tensor(np.asarray(a, np.float64), dtype=ott.DT, requires_grad=True)
     leaves = dict(positions=T(g["positions"]), rotations=T(g["rotations"]), scale=T(g["scale"]), weights=T(g["weights"]),
                   sensor_position=T(sc["sensors"][0]["position"]), sensor_rotation=T(sc["sensors"][0]["rotation"]))
+    stage = [dict(positions=T(gl["positions"]), rotations=T(gl["rotations"])) for gl in sc["groups"][1:]]
+    leaves["stage"] = stage
     s, v = T(src), T(val)
     img = ott.render(sc, leaves, s, v, stype, 0)
     (img * torch.tensor(G, dtype=ott.DT).reshape(img.shape)).sum().backward()
     gnp = lambda t: t.grad.numpy() if t.grad is not None else np.zeros(tuple(t.shape))
-    out = {k: gnp(t) for k, t in leaves.items()}
+    out = {k: gnp(t) for k, t in leaves.items() if k != "stage"}
     out.update(sources=gnp(s), values=gnp(v))
+    for i, st in enumerate(stage):
+        out[f"stage{i}_positions"], out[f"stage{i}_rotations"] = gnp(st["positions"]), gnp(st["rotations"])
     return img.detach().numpy(), out
 
 
@@ -151,4 +160,4 @@ def test_two_stage_gradients_through_the_secondary(polygon_secondary):
     assert oimg.sum() > 1.0
     np.testing.assert_allclose(img, oimg, rtol=5e-3, atol=2e-4 * oimg.max())
     _check(got, want, ["rotations", "positions", "scale", "weights", "values", "sources", "sensor_position",
-                       "sensor_rotation"], 1e-2)
+                       "sensor_rotation", "stage0_positions", "stage0_rotations"], 1e-2)
