@@ -11,7 +11,7 @@ import yaml
 from .. import random as R
 from ..core import (AsphericSurface, Box, Cylinder, DiskAperture, OrientedBox, PolygonAperture, Sphere, Triangle,
                     group_obstructions)
-from ..sensors import HexagonalSensor, SquareSensor
+from ..sensors import (DifferentiableHexagonalSensor, DifferentiableSquareSensor, HexagonalSensor, SquareSensor)
 from ..telescope import Mirror, Telescope, group_mirrors
 
 try:  # libyaml makes the 32 k-line CT5 file load in well under a second
@@ -91,4 +91,15 @@ def _parse_sensor(config):
         centers = np.array([config["centers_x"], config["centers_y"]], dtype=np.float32).T
         return HexagonalSensor(position=config["position"], rotation=config["orientation"], hex_centers=centers,
                                edge_width=edge_width)
+    # extension over the reference schema: the soft (Gaussian-splat) sensors are YAML-constructible
+    if stype == "differentiable_square":
+        return DifferentiableSquareSensor(position=config["position"], rotation=config["orientation"],
+                                          width=config["width"], height=config["height"],
+                                          bounds=tuple(config.get("bounds", (-1, 1, -1, 1))),
+                                          sigma=config.get("sigma", 0.1), kernel_size=config.get("kernel_size", 2))
+    if stype == "differentiable_hexagonal":
+        centers = np.array([config["centers_x"], config["centers_y"]], dtype=np.float32).T
+        return DifferentiableHexagonalSensor(position=config["position"], rotation=config["orientation"],
+                                             hex_centers=centers, sigma=config.get("sigma", 0.5),
+                                             kernel_size=config.get("kernel_size", 1))
     raise ValueError(f"Unknown sensor type: {stype}")

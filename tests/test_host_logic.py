@@ -206,3 +206,36 @@ def test_public_intersection_functions_match_reference_goldens():
     g = G["unit/plane"]
     assert np.array_equal(p[:, 0] > 1e9, g[:, 0] > 1e9)
     np.testing.assert_allclose(p[g[:, 0] < 1e9], g[g[:, 0] < 1e9], rtol=1e-4, atol=1e-5)
+
+
+def test_config_builder_and_soft_sensor_yaml(tmp_path, capsys):
+    from iactrace_b200.io import TelescopeConfigBuilder, build_telescope
+    from iactrace_b200.sensors import DifferentiableHexagonalSensor, DifferentiableSquareSensor
+    from iactrace_b200.utils import show_structure, trainable
+    b = (TelescopeConfigBuilder("demo").add_mirror_template("m", 0.05, -1.0, [])
+         .add_mirror_circular("A", "m", [2, 0, 0], [0, 0, 0], 1.0, offset=[2, 0])
+         .add_mirror_polygon("B", "m", [0, 2, 0], [0, 0, 0], [[-0.5, -0.5], [0.5, -0.5], [0.5, 0.5], [-0.5, 0.5]])
+         .add_mirror_circular("S", "m", [0, 0, 6], [180, 0, 0], 1.0, stage=1)
+         .add_obstruction_cylinder("c", [0, 0, 1], [0, 0, 2], 0.1).add_obstruction_box("b", [1, 1, 1], [2, 2, 2])
+         .add_obstruction("s", "sphere", center=[0, 1, 3], r=0.2)
+         .add_obstruction("t", "triangle", v0=[0, 0, 4], v1=[1, 0, 4], v2=[0, 1, 4])
+         .add_square_sensor_array("sq", [0, 0, -1], [0, 0, 0], 8, 4, [-1, 1, -0.5, 0.5], edge_width=0.01)
+         .add_square_sensor_array("soft", [0, 0, -1], [0, 0, 0], 8, 4, [-1, 1, -0.5, 0.5], soft=dict(sigma=0.3, kernel_size=1))
+         .add_hexagon_sensor_array("hx", [0, 0, -1], [0, 0, 0], [0.0, 0.1, 0.05, -0.05], [0.0, 0.0, 0.0866, 0.0866],
+                                   soft=dict(sigma=0.5, kernel_size=1)))
+    with pytest.raises(KeyError):
+        b.add_mirror_circular("X", "nope", [0, 0, 0], [0, 0, 0], 1.0)
+    with pytest.raises(ValueError):
+        b.add_obstruction("z", "torus", r=1)
+    path = b.save(tmp_path / "demo.yaml", precision=6)
+    tel = build_telescope(yaml.safe_load(path.read_text()), None, None)
+    assert tel.name == "demo" and [g.optical_stage for g in tel.mirror_groups] == [0, 0, 1]
+    assert [g.kind for g in tel.mirror_groups] == ["disk", "polygon", "disk"]
+    assert isinstance(tel.sensors[1], DifferentiableSquareSensor) and tel.sensors[1].sigma == 0.3
+    assert isinstance(tel.sensors[2], DifferentiableHexagonalSensor) and tel.sensors[2].n_pixels == 4
+    assert tel.sensors[0].edge_width == 0.01 and tel.get_obstruction_count() == 4
+    show_structure(tel)
+    out = capsys.readouterr().out
+    assert "mirror_groups.0.rotations: (1, 3) float32" in out and "sensors.0.position" in out
+    leaves = trainable(tel, "mirror_groups.*.rotations")
+    assert len(leaves) == 3 and all(t.requires_grad for _, t in leaves)
