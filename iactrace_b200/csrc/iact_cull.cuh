@@ -259,7 +259,7 @@ size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
         fl += (d.sens.tq * d.sens.tr + 1) / 2;
     }
     size_t bytes = fl * 4;
-    if (d.cull) bytes += (size_t)nwarps * ((n_obs + 1) & ~1) * 2 + (size_t)nwarps * IACT_HOIST_MAX * CYL_PACKED * sizeof(float) + 32;
+    if (d.cull) bytes += (size_t)nwarps * ((n_obs + 1) & ~1) * 2 + (size_t)nwarps * IACT_HOIST_MAX * sizeof(CylInv) + 32;
     return bytes + 16;
 }
 

@@ -150,10 +150,10 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     unsigned short* list = cull ? reinterpret_cast<unsigned short*>(p) + (size_t)warp * ((n_obs + 1) & ~1) : nullptr;
-    float* hoist = nullptr;
+    CylInv* hoist = nullptr;
     if (cull) {
         uintptr_t q = reinterpret_cast<uintptr_t>(reinterpret_cast<unsigned short*>(p) + (size_t)nwarps * ((n_obs + 1) & ~1));
-        hoist = reinterpret_cast<float*>((q + 31) & ~(uintptr_t)31) + (size_t)warp * IACT_HOIST_MAX * CYL_PACKED;
+        hoist = reinterpret_cast<CylInv*>((q + 31) & ~(uintptr_t)31) + (size_t)warp * IACT_HOIST_MAX;
     }
     __syncthreads();
 
@@ -178,7 +178,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             const float4 bnd = __ldg(sc.bounds + f);
             V3 d0;
             const bool uni = pair_direction<SRC>(bnd, src, d0);     // one direction for the whole pair?
-            const float* hoisted = nullptr;
+            const CylInv* hoisted = nullptr;
             if (cull) {
                 const Beam beam = make_beam<SRC>(bnd, src);
                 const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
@@ -187,11 +187,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 if (uni && n_list_cyl <= IACT_HOIST_MAX) {
                     // direction-only part of every listed cylinder test, once per pair (one lane per cylinder)
                     if (lane < n_list_cyl) {
-                        const float4* c = reinterpret_cast<const float4*>(ob.cyl + CYL_STRIDE * list[lane]);
-                        const float4 c0 = c[0], c1 = c[1];
-                        float4* w = reinterpret_cast<float4*>(hoist + CYL_PACKED * lane);
-                        w[0] = c0; w[1] = c1;
-                        *reinterpret_cast<CylInv*>(w + 2) = cyl_invariants(-d0, v3(c0.w, c1.x, c1.y));
+                        const float* c = ob.cyl + CYL_STRIDE * list[lane];
+                        hoist[lane] = cyl_invariants(-d0, v3(c[3], c[4], c[5]));
                     }
                     __syncwarp();
                     hoisted = hoist;
