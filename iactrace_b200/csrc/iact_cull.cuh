@@ -37,23 +37,6 @@ __device__ __forceinline__ Beam make_beam(float4 bnd, V3 src) {
     return b;
 }
 
-// Direction shared by all rays of a (facet, source) pair, when there is one: parallel sources always
-// (render.py:132-133); point sources whose parallax across the facet, R/D, is below half a float32 ulp
-// -- there the reference's per-ray normalize(p - src) (render.py:130-131) differs from the value at the
-// facet centre only by the rounding of p - src, so it is evaluated once per pair.  Returns d (the
-// propagation direction) and whether it is pair-uniform.
-#define IACT_HOIST_MAX 16          // cylinders per warp list whose direction invariants are hoisted
-template <int SRC>
-__device__ __forceinline__ bool pair_direction(float4 bnd, V3 src, V3& d0) {
-    if (SRC != IACT_SOURCE_POINT) { d0 = src; return true; }
-    const V3 a = v3(bnd.x, bnd.y, bnd.z) - src;
-    const float n2 = dot(a, a);
-    if (!(n2 > 1e-30f && n2 < 1e37f)) { d0 = a; return false; }
-    const float inv = frsqrt_nr(n2);
-    d0 = inv * a;
-    return bnd.w * inv < 5.9e-8f;
-}
-
 // Conservative: false only if no ray of the beam can come within r of the segment [p1,p2].
 // A ray starts within R of c and its direction is within `spread` (chord) + 1.5708 R/D (point-source
 // parallax) of u; rays are half-lines, so everything behind the facet is out of reach.
@@ -259,7 +242,7 @@ size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
         fl += (d.sens.tq * d.sens.tr + 1) / 2;
     }
     size_t bytes = fl * 4;
-    if (d.cull) bytes += (size_t)nwarps * ((n_obs + 1) & ~1) * 2 + (size_t)nwarps * IACT_HOIST_MAX * sizeof(CylInv) + 32;
+    if (d.cull) bytes += (size_t)nwarps * ((n_obs + 1) & ~1) * 2;
     return bytes + 16;
 }
 

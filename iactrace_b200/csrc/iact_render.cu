@@ -150,11 +150,6 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     unsigned short* list = cull ? reinterpret_cast<unsigned short*>(p) + (size_t)warp * ((n_obs + 1) & ~1) : nullptr;
-    CylInv* hoist = nullptr;
-    if (cull) {
-        uintptr_t q = reinterpret_cast<uintptr_t>(reinterpret_cast<unsigned short*>(p) + (size_t)nwarps * ((n_obs + 1) & ~1));
-        hoist = reinterpret_cast<CylInv*>((q + 31) & ~(uintptr_t)31) + (size_t)warp * IACT_HOIST_MAX;
-    }
     __syncthreads();
 
     const int M = sc.M;
@@ -175,24 +170,11 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             const int f = f0 + fi;
             const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
             int n_list = 0, n_list_cyl = 0;
-            const float4 bnd = __ldg(sc.bounds + f);
-            V3 d0;
-            const bool uni = pair_direction<SRC>(bnd, src, d0);     // one direction for the whole pair?
-            const CylInv* hoisted = nullptr;
             if (cull) {
-                const Beam beam = make_beam<SRC>(bnd, src);
+                const Beam beam = make_beam<SRC>(__ldg(sc.bounds + f), src);
                 const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
                 if (cnt.x >= 0) n_list = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, n_list_cyl);
                 else            n_list = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, n_list_cyl);
-                if (uni && n_list_cyl <= IACT_HOIST_MAX) {
-                    // direction-only part of every listed cylinder test, once per pair (one lane per cylinder)
-                    if (lane < n_list_cyl) {
-                        const float* c = ob.cyl + CYL_STRIDE * list[lane];
-                        hoist[lane] = cyl_invariants(-d0, v3(c[3], c[4], c[5]));
-                    }
-                    __syncwarp();
-                    hoisted = hoist;
-                }
             }
             const float4* tab = sc.world + ((size_t)f * M) * 2;
             PixCache cache;
@@ -205,13 +187,15 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 V3 o = v3(a.x, a.y, a.z);
                 const V3 n = v3(b.x, b.y, b.z);
                 // render.py:129-133
-                V3 d = d0;
-                if (SRC == IACT_SOURCE_POINT && !uni) {
+                V3 d;
+                if (SRC == IACT_SOURCE_POINT) {
                     d = o - src;
                     d = frsqrt_nr(dot(d, d)) * d;
+                } else {
+                    d = src;
                 }
                 // render.py:138 shadow of the incoming leg (infinite ray back towards the source)
-                const bool blocked = occluded(ob, o, -d, list, n_list_cyl, n_list, hoisted);
+                const bool blocked = occluded(ob, o, -d, list, n_list_cyl, n_list);
                 // render.py:140-141, reflection.py:17-19
                 const float c = dot(d, n);
                 d = d - (2.0f * c) * n;
