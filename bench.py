@@ -33,7 +33,6 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
-sys.path.insert(0, str(ROOT / "tests"))
 
 # Brute-force algorithmic flops per ray (FMA = 2): fixed part + per-primitive tests.
 F_FIXED = {("hex", "point"): 104, ("square", "point"): 76, ("hex", "parallel"): 92, ("square", "parallel"): 64}
@@ -56,13 +55,10 @@ DEFAULT_WORKLOAD = "ct5_point_4096x115_hex"
 
 
 def make_sources(w, rank=0):
-    from _bridge import point_grid, parallel_grid
+    from iactrace_b200.workloads import point_grid, parallel_grid, star_field
     kind, n_side, ang = w["grid"]
     if kind == "stars":  # Cassegrain.ipynb cell 8: uniform directions in a 3 deg box, z = -1, normalised
-        rng = np.random.default_rng(42 + rank)
-        f = np.deg2rad(ang)
-        d = np.stack([rng.uniform(-f / 2, f / 2, n_side), rng.uniform(-f / 2, f / 2, n_side), -np.ones(n_side)], 1)
-        return (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32), "parallel"
+        return star_field(n_side, ang, seed=42 + rank)[0], "parallel"
     if kind == "point":
         src = point_grid(n_side, ang)
         if rank:  # rank-specific sub-pixel shift of the field angles (weak scaling: distinct work per rank)
@@ -77,7 +73,7 @@ def make_sources(w, rank=0):
 
 def load_scene_config(name):
     if name == "cassegrain":
-        from _bridge import cassegrain_config
+        from iactrace_b200.workloads import cassegrain_config
         return cassegrain_config(True)
     from iactrace_b200.io import load_packed_config
     return load_packed_config(name)
@@ -222,7 +218,8 @@ def main():
     src_np, stype = make_sources(w, rank)
     val_np = np.ones(len(src_np), np.float32)
     if w["grid"][0] == "stars":
-        val_np = (10 ** (-10 * np.random.default_rng(4242).uniform(size=len(src_np)))).astype(np.float32)
+        from iactrace_b200.workloads import star_field
+        val_np = star_field(len(src_np))[1]
     src_host = torch.from_numpy(src_np).pin_memory()
     val_host = torch.from_numpy(val_np).pin_memory()
     src_dev, val_dev = src_host.to(dev), val_host.to(dev)
