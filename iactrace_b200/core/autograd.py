@@ -54,8 +54,9 @@ class _Render(torch.autograd.Function):
         stages = _get_stages(tel.mirror_groups)
         g_img = contig(g_img.to(torch.float32))
         dev = src.device
-        g_src = torch.zeros_like(src)
-        g_val = torch.zeros_like(val)
+        need = ctx.needs_input_grad          # (tel, source_type, sensor_idx, src, val, *leaves)
+        g_src = torch.zeros_like(src) if need[3] else None
+        g_val = torch.zeros_like(val) if need[4] else None
         g_spos = torch.zeros(3, device=dev)
         g_srot = torch.zeros(3, device=dev)
         later = [g for k in stages if k != 0 for g in stages[k]]
@@ -66,10 +67,14 @@ class _Render(torch.autograd.Function):
         keep = []
         sc, _ = build_scene(tel, sensor_idx, keep)
         off = 0
+        li = 5                               # index of this group's first leaf in `need`
         for g in stages.get(0, []):
             F, M = len(g), g.points.shape[1]
             gp, gr = torch.zeros((F, 3), device=dev), torch.zeros((F, 3), device=dev)
-            gs, gw = torch.zeros((F,), device=dev), torch.zeros((F, M, 1), device=dev)
+            gs = torch.zeros((F,), device=dev)
+            # per-sample weight gradients cost one global atomic per ray: only when asked for
+            gw = torch.zeros((F, M, 1), device=dev) if need[li + 3] else None
+            li += 4
             if sc is not None and F * M:
                 fa = g._facets_struct(keep)
                 sub = N.IactScene.from_buffer_copy(sc)
