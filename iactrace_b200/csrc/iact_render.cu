@@ -88,6 +88,43 @@ __device__ __forceinline__ void warp_hist_add(float* hist, int pix, float val) {
     }
 }
 
+// DifferentiableHexagonalSensor.accumulate for a whole warp at once: every lane walks the same tap
+// order, and each tap goes through warp_hist_add (the rays of one (facet, source) pair share their
+// base hexagon, so per-lane shared atomics would serialise 32-way on every tap).  `active` = this
+// lane has a hit to splat.  Must be called by all 32 lanes.
+template <typename LUT>
+__device__ __forceinline__ void splat_soft_hex_warp(const SensDev& se, const LUT* lut, bool active, float x, float y, float val,
+                                                    float* hist) {
+    float xg, yg; hex_grid_coords(se, x, y, xg, yg);
+    const float q = se.ax_qx * xg - se.ax_qy * yg, r = se.ax_ry * yg;
+    float qb, rb; hex_round(q, r, qb, rb);
+    active = active && (fabsf(qb) < 1e6f) && (fabsf(rb) < 1e6f);
+    if (!__any_sync(0xffffffffu, active)) return;
+    const float ddx = xg - se.size_sqrt3 * (qb + rb * 0.5f), ddy = yg - se.size_1p5 * rb;
+    const int K = se.ksize;
+    const float inv_sigma = 1.0f / se.sigma;
+    float wsum = 0.f;
+    for (int oq = -K; oq <= K; ++oq)
+        for (int orr = -K; orr <= K; ++orr) {
+            if (max(max(abs(oq), abs(orr)), abs(oq + orr)) > K) continue;
+            const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
+            const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
+            const float z = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) * se.inv_inradius * inv_sigma;
+            wsum += expf(-0.5f * z * z);
+        }
+    const float scale = active ? val / wsum : 0.f;
+    for (int oq = -K; oq <= K; ++oq)
+        for (int orr = -K; orr <= K; ++orr) {
+            if (max(max(abs(oq), abs(orr)), abs(oq + orr)) > K) continue;
+            const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
+            const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
+            const float z = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) * se.inv_inradius * inv_sigma;
+            const float w = expf(-0.5f * z * z);
+            const int pix = active ? hex_lookup(se, lut, qb + (float)oq, rb + (float)orr) : -1;
+            warp_hist_add(hist, pix, scale * w);
+        }
+}
+
 // Per-warp-item pixel cache: the rays of one (facet, source) pair land in 1-3 hex pixels, so the warp
 // keeps up to three (pixel, per-lane partial sum) slots in registers across all its iterations and
 // touches the shared histogram once per slot at the end of the item; rays outside the three cached
@@ -223,7 +260,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 } else {
                     const bool add = live && val != 0.f;
                     if (SENS == SENS_HEX) {
-                        if (soft) { if (add) splat_soft_hex(sc.sens, lut, x, y, val, hist); }
+                        if (soft) splat_soft_hex_warp(sc.sens, lut, add, x, y, val, hist);
                         else cache.add(hist, add ? hex_pixel(sc.sens, lut, x, y) : -1, val);
                     } else if (add) {
                         if (soft) splat_soft_square(sc.sens, x, y, val, gout);
