@@ -127,3 +127,42 @@ def test_primitives_match_reference():
     m = np.isfinite(GOLD["unit/surf_t"])
     np.testing.assert_allclose(pt[m], GOLD["unit/surf_pt"][m], atol=2e-6)
     np.testing.assert_allclose(n[m], GOLD["unit/surf_n"][m], atol=2e-6)
+
+
+@pytest.mark.skipif(not Path("/root/reference/iactrace/core/render.py").exists(), reason="reference tree not present")
+def test_committed_fixtures_are_what_the_reference_produces(tmp_path):
+    """In the build container: re-run a slice of tests/golden/make_golden.py (the reference's own
+    sources on oracle/jaxshim) in a subprocess and compare with the committed fixtures."""
+    import subprocess
+    import sys
+    root = Path(__file__).resolve().parent.parent
+    code = f"""
+import sys, tempfile, yaml, numpy as np
+sys.path[:0] = [r"{root / 'oracle' / 'jaxshim'}", "/root/reference", r"{root}", r"{root / 'tests'}"]
+import jax, jax.numpy as jnp
+from jax import random as jrandom
+from iactrace import MCIntegrator, Telescope
+from oracle import prng
+from golden.cases import CASES, case_values
+out = {{}}
+for name in ("ct3_point", "cassegrain"):
+    c = CASES[name]
+    jrandom.MODE = prng.PARTITIONABLE if c["mode"] == "partitionable" else prng.LEGACY
+    with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as f:
+        yaml.safe_dump(c["cfg"](), f)
+    tel = Telescope.from_yaml(f.name, MCIntegrator(c["M"]), key=jax.random.key(c["seed"]))
+    if c["rough"]:
+        tel = tel.apply_roughness(c["rough"])
+    si = c["sensors"][0]
+    pts, vals = tel(jnp.asarray(c["src"]), jnp.asarray(case_values(name)), c["stype"], sensor_idx=si, debug=True)
+    out[name + "/pts"], out[name + "/vals"] = np.asarray(pts), np.asarray(vals)
+    out[name + "/points"] = np.asarray(tel.mirror_groups[0].points)
+np.savez(r"{tmp_path / 'regen.npz'}", **out)
+"""
+    subprocess.run([sys.executable, "-W", "ignore", "-c", code], check=True, timeout=300)
+    regen = np.load(tmp_path / "regen.npz")
+    for name in ("ct3_point", "cassegrain"):
+        si = CASES[name]["sensors"][0]
+        assert np.array_equal(regen[name + "/pts"], GOLD[f"{name}/s{si}/debug_pts"])
+        assert np.array_equal(regen[name + "/vals"], GOLD[f"{name}/s{si}/debug_vals"])
+        assert np.array_equal(regen[name + "/points"], GOLD[f"{name}/group0/points"])
