@@ -1,0 +1,69 @@
+"""Two real GPUs over NCCL: the source-sharded render + all-reduce equals the single-GPU render, and
+the row-sharded response matrix tiles the full matrix.  Skipped with fewer than two devices."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import iactrace_b200 as I
+        from iactrace_b200.io import build_telescope, load_packed_config
+        from iactrace_b200.parallel import render_sharded, response_matrix_sharded
+        from iactrace_b200.workloads import point_grid
+        cfg = load_packed_config("CT3")
+        cfg = dict(cfg, mirrors=cfg["mirrors"][::6])
+        tel = build_telescope(cfg, I.MCIntegrator(32), I.random.key(0))      # same key on every rank -> same samples
+        src = torch.from_numpy(point_grid(7, 1.0)).cuda()
+        val = torch.linspace(0.5, 1.5, len(src), device="cuda")
+        img = render_sharded(tel, src, val, "point", 0)
+        full, _ = response_matrix_sharded(tel, src, val, "point", 0, gather=True)
+        rows, (a, b) = response_matrix_sharded(tel, src, val, "point", 0)
+        torch.cuda.synchronize()
+        q.put((rank, img.cpu().numpy(), full.cpu().numpy(), rows.cpu().numpy(), a, b,
+               tel.mirror_groups[0].points[:2, :3].cpu().numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_gpu_sharded_render_matches_single_gpu():
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    import iactrace_b200 as I
+    from iactrace_b200.core import render, render_response_matrix
+    from iactrace_b200.io import build_telescope, load_packed_config
+    from iactrace_b200.workloads import point_grid
+    cfg = load_packed_config("CT3")
+    cfg = dict(cfg, mirrors=cfg["mirrors"][::6])
+    tel = build_telescope(cfg, I.MCIntegrator(32), I.random.key(0))
+    src = torch.from_numpy(point_grid(7, 1.0)).cuda()
+    val = torch.linspace(0.5, 1.5, len(src), device="cuda")
+    want = render(tel, src, val, "point", 0).cpu().numpy()
+    want_m = render_response_matrix(tel, src, val, "point", 0).cpu().numpy()
+    assert np.array_equal(res[0][6], res[1][6])                   # identical samples on both ranks
+    for rank, img, full, rows, a, b, _ in res:
+        np.testing.assert_allclose(img, want, rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(full, want_m, rtol=2e-6, atol=1e-9)
+        np.testing.assert_allclose(rows, want_m[a:b], rtol=2e-6, atol=1e-9)
+    assert (res[0][4], res[0][5], res[1][4], res[1][5]) == (0, 25, 25, 49)
