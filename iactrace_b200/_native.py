@@ -48,6 +48,7 @@ class IactSensor(C.Structure):
 
 class IactScene(C.Structure):
     _fields_ = [("n_facets", C.c_int32), ("n_samples", C.c_int32), ("world", _fp), ("bounds", _fp),
+                ("chunk_bounds", _fp),
                 ("n_cyl", C.c_int32), ("cyl_p1", _fp), ("cyl_p2", _fp), ("cyl_r", _fp),
                 ("n_box", C.c_int32), ("box_p1", _fp), ("box_p2", _fp),
                 ("n_sph", C.c_int32), ("sph_c", _fp), ("sph_r", _fp),
@@ -82,6 +83,7 @@ _SIGNATURES = {
     "iact_random_normal": (C.c_int, [_KEY, C.c_int, C.c_int, _fp, _fp]),
     "iact_random_uniform": (C.c_int, [_KEY, C.c_int, C.c_int, C.c_float, C.c_float, _fp, _fp]),
     "iact_transform_to_world": (C.c_int, [C.POINTER(IactFacets), C.c_int, _fp, _fp, _fp]),
+    "iact_transform_to_world_binned": (C.c_int, [C.POINTER(IactFacets), C.c_int, C.c_int, _fp, _fp, _fp, _fp]),
     "iact_render": (C.c_int, [C.POINTER(IactScene), _fp, _fp, C.c_int, C.c_int, _fp, _fp]),
     "iact_response_matrix": (C.c_int, [C.POINTER(IactScene), _fp, _fp, C.c_int, C.c_int, _fp, _fp]),
     "iact_render_debug": (C.c_int, [C.POINTER(IactScene), _fp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, _fp]),

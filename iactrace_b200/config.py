@@ -8,3 +8,8 @@ cull_obstructions = True
 # Return NumPy arrays (device -> host copy + synchronisation) instead of torch CUDA tensors from
 # render / render_debug / render_response_matrix.  Off by default: outputs stay on the GPU, stream-ordered.
 return_numpy = False
+
+# From this many samples per facet on, the world table is written in spatially binned order
+# (iact_transform_to_world_binned) and the trace kernel culls again per 32-sample run.  Below it the
+# per-iteration test costs more than it saves.  0 disables binning.
+bin_samples_min = 256

@@ -34,10 +34,12 @@ def _world_tables(tel, stage0):
     srcs = []
     for g in stage0:
         srcs += [g.positions, g.rotations, g.perturbation_scale, g.points, g.normals, g.perturbation_delta, g.weights]
-    sig = _tensor_sig(srcs)
+    M0 = stage0[0].points.shape[1]
+    binned = bool(config.bin_samples_min) and M0 >= config.bin_samples_min
+    sig = (_tensor_sig(srcs), binned)
     hit = tel._cache.get("world")
     if hit is not None and hit[0] == sig:
-        return hit[1], hit[2]
+        return hit[1], hit[2], hit[3]
     M = stage0[0].points.shape[1]
     for g in stage0:
         if g.points.shape[1] != M:
@@ -46,16 +48,22 @@ def _world_tables(tel, stage0):
     dev = stage0[0].points.device
     world = torch.empty((F, M, 8), dtype=torch.float32, device=dev)
     bounds = torch.empty((F, 4), dtype=torch.float32, device=dev)
+    chunks = torch.empty((F, (M + 31) // 32, 4), dtype=torch.float32, device=dev) if binned else None
+    grid_side = max(1, min(16, int(round(math.sqrt(M / 32.0)))))
     off = 0
     for g in stage0:
         keep = []
         if len(g) * M:
             fa = g._facets_struct(keep)
-            N.check(N.lib().iact_transform_to_world(fa, off, N.ptr(world), N.ptr(bounds), N.stream_ptr()),
-                    "transform_to_world")
+            if binned:
+                N.check(N.lib().iact_transform_to_world_binned(fa, off, grid_side, N.ptr(world), N.ptr(bounds),
+                                                               N.ptr(chunks), N.stream_ptr()), "transform_to_world_binned")
+            else:
+                N.check(N.lib().iact_transform_to_world(fa, off, N.ptr(world), N.ptr(bounds), N.stream_ptr()),
+                        "transform_to_world")
         off += len(g)
-    tel._cache["world"] = (sig, world, bounds)
-    return world, bounds
+    tel._cache["world"] = (sig, world, bounds, chunks)
+    return world, bounds, chunks
 
 
 def _stage_tables(tel, groups, dev):
@@ -118,10 +126,10 @@ def build_scene(tel, sensor_idx: int, keep: list, cull: bool | None = None):
     if not stages or 0 not in stages:
         return None, sensor
     sc = N.IactScene()
-    world, bounds = _world_tables(tel, stages[0])
-    keep += [world, bounds]
+    world, bounds, chunks = _world_tables(tel, stages[0])
+    keep += [world, bounds, chunks]
     sc.n_facets, sc.n_samples = world.shape[0], world.shape[1]
-    sc.world, sc.bounds = N.ptr(world), N.ptr(bounds)
+    sc.world, sc.bounds, sc.chunk_bounds = N.ptr(world), N.ptr(bounds), N.ptr(chunks)
     dev = world.device
     tabs = _obstruction_tables(tel)
     for name, fields in (("cyl", ("cyl_p1", "cyl_p2", "cyl_r")), ("box", ("box_p1", "box_p2")),

@@ -204,6 +204,7 @@ int fill_scene(const IactScene* s, SceneDev& d) {
     memset(&d, 0, sizeof(d));
     d.F = s->n_facets; d.M = s->n_samples;
     d.world = reinterpret_cast<const float4*>(s->world); d.bounds = reinterpret_cast<const float4*>(s->bounds);
+    d.chunk_bounds = reinterpret_cast<const float4*>(s->chunk_bounds);
     d.n_cyl = s->n_cyl; d.cyl_p1 = s->cyl_p1; d.cyl_p2 = s->cyl_p2; d.cyl_r = s->cyl_r;
     d.n_box = s->n_box; d.box_p1 = s->box_p1; d.box_p2 = s->box_p2;
     d.n_sph = s->n_sph; d.sph_c = s->sph_c; d.sph_r = s->sph_r;

@@ -216,11 +216,19 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             const float4* tab = sc.world + ((size_t)f * M) * 2;
             PixCache cache;
             cache.reset();
+            // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
+            const bool sub_beams = cull && sc.chunk_bounds != nullptr && n_list > 0 && n_list <= 32;
+            const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
             for (int mb = m0; mb < m1; mb += 32) {
                 const int m = mb + lane;
                 const bool live = m < m1;
                 const int mm = live ? m : m1 - 1;
                 const float4 a = __ldg(tab + 2 * mm), b = __ldg(tab + 2 * mm + 1);
+                unsigned sub_mask = 0xffffffffu;
+                if (sub_beams) {
+                    const Beam cb = make_beam<SRC>(__ldg(cbs + (mb >> 5)), src);
+                    sub_mask = __ballot_sync(0xffffffffu, lane < n_list && (!cb.ok || keep_primitive(ob, cb, list[lane])));
+                }
                 V3 o = v3(a.x, a.y, a.z);
                 const V3 n = v3(b.x, b.y, b.z);
                 // render.py:129-133
@@ -232,7 +240,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                     d = src;
                 }
                 // render.py:138 shadow of the incoming leg (infinite ray back towards the source)
-                const bool blocked = occluded(ob, o, -d, list, n_list_cyl, n_list);
+                const bool blocked = sub_beams ? occluded_masked(ob, o, -d, list, n_list_cyl, sub_mask)
+                                               : occluded(ob, o, -d, list, n_list_cyl, n_list);
                 // render.py:140-141, reflection.py:17-19
                 const float c = dot(d, n);
                 d = d - (2.0f * c) * n;
@@ -249,7 +258,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 plane_hit(sc.sens, o, d, x, y);
                 if (MODE == MODE_DEBUG) {
                     if (live) {
-                        const size_t ri = ((size_t)f * plan.S + s) * M + m;
+                        const size_t ri = ((size_t)f * plan.S + s) * M + __float_as_int(b.w);   // original sample index
                         out[2 * ri] = x; out[2 * ri + 1] = y; out_val[ri] = val;
                         if (out_pix) {
                             int pix = -1;

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) transform_kernel(const IactFacets fa, int
         V3 nw = mul(R, nl) + scale * mul(R, dl);
         nw = (1.0f / sqrtf(dot(nw, nw))) * nw;
         out[2 * m] = make_float4(pw.x, pw.y, pw.z, 1.0f / fa.weights[(size_t)f * M + m]);   // value = v cos / w (render.py:141)
-        out[2 * m + 1] = make_float4(nw.x, nw.y, nw.z, 0.f);
+        out[2 * m + 1] = make_float4(nw.x, nw.y, nw.z, __int_as_float(m));
         const V3 dd = pw - pos;
         maxd2 = fmaxf(maxd2, dot(dd, dd));
     }
@@ -151,6 +151,94 @@ __global__ void __launch_bounds__(256) transform_kernel(const IactFacets fa, int
         float* b = bounds + 4 * (size_t)(facet_offset + f);
         b[0] = pos.x; b[1] = pos.y; b[2] = pos.z;
         b[3] = sqrtf(red[0]) * 1.00001f + 1e-6f;
+    }
+}
+
+// Binned variant: counting sort of the facet's samples into G x G cells (serpentine order) before the
+// transform, so that 32 consecutive rows form a compact patch; then one bounding sphere per run of 32.
+__global__ void __launch_bounds__(256) transform_binned_kernel(const IactFacets fa, int facet_offset, int G,
+                                                               float* world, float* bounds, float* chunk_bounds) {
+    const int f = blockIdx.x;
+    const M33 R = euler_to_matrix(fa.rotations[3 * f], fa.rotations[3 * f + 1], fa.rotations[3 * f + 2]);
+    const V3 pos = ld3(fa.positions + 3 * f);
+    const float scale = fa.scale[f];
+    const int M = fa.n_samples;
+    float4* out = reinterpret_cast<float4*>(world) + ((size_t)(facet_offset + f) * M) * 2;
+    __shared__ float red[4][256];
+    __shared__ int count[256], cursor[256];
+    // local bounding box of the sample points
+    float xmin = INFINITY, xmax = -INFINITY, ymin = INFINITY, ymax = -INFINITY;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const size_t i = ((size_t)f * M + m) * 3;
+        const float x = fa.points[i], y = fa.points[i + 1];
+        xmin = fminf(xmin, x); xmax = fmaxf(xmax, x); ymin = fminf(ymin, y); ymax = fmaxf(ymax, y);
+    }
+    red[0][threadIdx.x] = xmin; red[1][threadIdx.x] = -xmax; red[2][threadIdx.x] = ymin; red[3][threadIdx.x] = -ymax;
+    count[threadIdx.x] = 0;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) for (int k = 0; k < 4; ++k) red[k][threadIdx.x] = fminf(red[k][threadIdx.x], red[k][threadIdx.x + s]);
+        __syncthreads();
+    }
+    xmin = red[0][0]; xmax = -red[1][0]; ymin = red[2][0]; ymax = -red[3][0];
+    const float sx = (float)G / fmaxf(xmax - xmin, 1e-20f), sy = (float)G / fmaxf(ymax - ymin, 1e-20f);
+    auto cell_of = [&](float x, float y) {
+        const int ix = min(G - 1, max(0, (int)((x - xmin) * sx))), iy = min(G - 1, max(0, (int)((y - ymin) * sy)));
+        return iy * G + ((iy & 1) ? G - 1 - ix : ix);               // serpentine: consecutive cells are neighbours
+    };
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const size_t i = ((size_t)f * M + m) * 3;
+        atomicAdd(&count[cell_of(fa.points[i], fa.points[i + 1])], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int c = 0; c < G * G; ++c) { cursor[c] = run; run += count[c]; }
+    }
+    __syncthreads();
+    float maxd2 = 0.f;
+    for (int m = threadIdx.x; m < M; m += blockDim.x) {
+        const size_t i = ((size_t)f * M + m) * 3;
+        const V3 pl = ld3(fa.points + i), nl = ld3(fa.normals + i), dl = ld3(fa.delta + i);
+        const int slot = atomicAdd(&cursor[cell_of(pl.x, pl.y)], 1);
+        const V3 pw = mul(R, pl) + pos;
+        V3 nw = mul(R, nl) + scale * mul(R, dl);
+        nw = (1.0f / sqrtf(dot(nw, nw))) * nw;
+        out[2 * slot] = make_float4(pw.x, pw.y, pw.z, 1.0f / fa.weights[(size_t)f * M + m]);
+        out[2 * slot + 1] = make_float4(nw.x, nw.y, nw.z, __int_as_float(m));
+        const V3 dd = pw - pos;
+        maxd2 = fmaxf(maxd2, dot(dd, dd));
+    }
+    red[0][threadIdx.x] = maxd2;
+    __syncthreads();                                               // also publishes the rows to the block
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) red[0][threadIdx.x] = fmaxf(red[0][threadIdx.x], red[0][threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float* b = bounds + 4 * (size_t)(facet_offset + f);
+        b[0] = pos.x; b[1] = pos.y; b[2] = pos.z;
+        b[3] = sqrtf(red[0][0]) * 1.00001f + 1e-6f;
+    }
+    // bounding sphere of every run of 32 rows: centre = bounding-box centre, radius = farthest row
+    const int n_chunks = (M + 31) / 32, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int k = warp; k < n_chunks; k += blockDim.x >> 5) {
+        const int m = min(32 * k + lane, M - 1);
+        const float4 a = out[2 * m];
+        float lo[3] = {a.x, a.y, a.z}, hi[3] = {a.x, a.y, a.z};
+        for (int o = 16; o > 0; o >>= 1)
+            for (int j = 0; j < 3; ++j) {
+                lo[j] = fminf(lo[j], __shfl_xor_sync(0xffffffffu, lo[j], o));
+                hi[j] = fmaxf(hi[j], __shfl_xor_sync(0xffffffffu, hi[j], o));
+            }
+        const V3 c = v3(0.5f * (lo[0] + hi[0]), 0.5f * (lo[1] + hi[1]), 0.5f * (lo[2] + hi[2]));
+        const V3 dd = v3(a.x, a.y, a.z) - c;
+        float r2 = dot(dd, dd);
+        for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+        if (lane == 0) {
+            float* cb = chunk_bounds + 4 * ((size_t)(facet_offset + f) * n_chunks + k);
+            cb[0] = c.x; cb[1] = c.y; cb[2] = c.z; cb[3] = sqrtf(r2) * 1.00001f + 1e-6f;
+        }
     }
 }
 
@@ -219,6 +307,19 @@ extern "C" int iact_random_normal(const uint32_t key[2], int rng_mode, int n, fl
 }
 extern "C" int iact_random_uniform(const uint32_t key[2], int rng_mode, int n, float lo, float hi, float* out, void* stream) {
     return launch_random(key, rng_mode, n, 0, lo, hi, out, stream);
+}
+
+extern "C" int iact_transform_to_world_binned(const IactFacets* fa, int facet_offset, int grid_side, float* world, float* bounds,
+                                              float* chunk_bounds, void* stream) {
+    IACT_REQUIRE(fa && world && bounds && chunk_bounds, "null pointer");
+    IACT_REQUIRE(fa->n_facets >= 0 && fa->n_samples >= 0 && facet_offset >= 0, "negative size");
+    IACT_REQUIRE(grid_side >= 1 && grid_side <= 16, "grid_side must be in [1, 16]");
+    if (fa->n_facets == 0 || fa->n_samples == 0) return IACT_OK;
+    IACT_REQUIRE(fa->positions && fa->rotations && fa->scale && fa->points && fa->normals && fa->delta && fa->weights,
+                 "null facet table");
+    transform_binned_kernel<<<fa->n_facets, 256, 0, (cudaStream_t)stream>>>(*fa, facet_offset, grid_side, world, bounds, chunk_bounds);
+    iact_count_launch();
+    return iact_check_cuda(cudaGetLastError(), "transform_binned_kernel launch");
 }
 
 extern "C" int iact_transform_to_world(const IactFacets* fa, int facet_offset, float* world, float* bounds, void* stream) {

@@ -96,8 +96,10 @@ typedef struct IactSensor {
 /* Everything a render needs.  `world`/`bounds` come from iact_transform_to_world. */
 typedef struct IactScene {
     int32_t      n_facets, n_samples;
-    const float* world;    /* device (F, M, 8): px,py,pz,1/weight, nx,ny,nz,0 */
+    const float* world;    /* device (F, M, 8): px,py,pz,1/weight, nx,ny,nz,(original sample index as int bits) */
     const float* bounds;   /* device (F, 4): bounding sphere of the facet's world points */
+    const float* chunk_bounds; /* device (F, ceil(M/32), 4) or NULL: bounding spheres of each run of 32 consecutive
+                                  table rows, as written by iact_transform_to_world_binned (enables per-iteration culling) */
     /* obstruction groups in the reference's fixed order (obstructions.py:258-278) */
     int32_t n_cyl;  const float *cyl_p1, *cyl_p2, *cyl_r;       /* (K,3)(K,3)(K,)   */
     int32_t n_box;  const float *box_p1, *box_p2;               /* (K,3)(K,3)       */
@@ -165,6 +167,15 @@ int iact_random_uniform(const uint32_t key[2], int rng_mode, int n, float lo, fl
  * [facet_offset, facet_offset + n_facets) of the packed world table + bounds. */
 int iact_transform_to_world(const IactFacets* facets, int facet_offset,
                             float* world /*device (Ftot,M,8): px,py,pz,1/w, nx,ny,nz,0*/, float* bounds /*device (Ftot,4)*/, void* stream);
+
+/* Same transform, but the rows of each facet are written in spatially binned order (counting sort of
+ * the samples into a grid_side x grid_side grid of cells over the facet, serpentine cell order), so that
+ * every run of 32 consecutive rows covers a small patch; chunk_bounds (Ftot, ceil(M/32), 4) receives the
+ * bounding sphere of each run.  Row slot [7] holds the original sample index (int bits), which
+ * iact_render_debug uses to keep the reference's output order.  Summation order aside, rendering from a
+ * binned table is identical to rendering from the plain one. */
+int iact_transform_to_world_binned(const IactFacets* facets, int facet_offset, int grid_side,
+                                   float* world, float* bounds, float* chunk_bounds, void* stream);
 
 /* render (core/render.py:174-220).  out_image: device (H,W) or (P,), OVERWRITTEN. */
 int iact_render(const IactScene* scene, const float* sources /*device (S,3)*/, const float* values /*device (S,)*/,

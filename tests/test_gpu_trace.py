@@ -169,6 +169,48 @@ def test_culling_fuzz_random_scenes():
     assert total_shadowed > 1000
 
 
+def test_binned_table_and_sub_beam_culling_are_exact():
+    """M >= 256: the world table is spatially binned and each 32-sample run is culled again.  Per-ray
+    output (in the reference's order) must equal both the brute-force kernel and the un-binned path."""
+    tel = _tel("CT5", 300, step=9)
+    cases = (("point", point_grid(3, 1.5)),
+             ("point", np.array([[3.0, -2.0, 60.0], [0.0, 0.0, 36.0], [-8.0, 5.0, 90.0]], np.float32)),
+             ("parallel", parallel_grid(3, 3.0)))
+    for stype, src in cases:
+        val = np.linspace(0.5, 1.5, len(src)).astype(np.float32)
+        out = {}
+        for name, cull, bin_min in (("binned+culled", True, 256), ("binned brute force", False, 256), ("plain+culled", True, 0)):
+            Rm.cull_obstructions, Rm.bin_samples_min = cull, bin_min
+            try:
+                xy, v, pix = render_debug(tel, src, val, stype, 0, return_pixels=True)
+                img = render(tel, src, val, stype, 0)
+                out[name] = (xy.cpu().numpy(), v.cpu().numpy(), pix.cpu().numpy(), img.cpu().numpy())
+            finally:
+                Rm.cull_obstructions, Rm.bin_samples_min = True, 256
+        ref = out["plain+culled"]
+        for name in ("binned+culled", "binned brute force"):
+            for a, b in zip(out[name][:3], ref[:3]):
+                assert np.array_equal(a, b), name
+            np.testing.assert_allclose(out[name][3], ref[3], rtol=2e-5, atol=1e-7 * ref[3].max())
+        assert 0.0 < (ref[1] == 0).mean() < 0.9
+    # chunk bounds really bound their rows
+    from iactrace_b200.core.render import build_scene
+    keep = []
+    sc, _ = build_scene(tel, 0, keep)
+    world, bounds, chunks = keep[0], keep[1], keep[2]
+    assert chunks is not None and chunks.shape == (world.shape[0], (300 + 31) // 32, 4)
+    p = world[..., 0:3]
+    for k in range(chunks.shape[1]):
+        rows = p[:, 32 * k:32 * k + 32]
+        d = (rows - chunks[:, k:k + 1, 0:3]).norm(dim=-1).max(dim=1).values
+        assert bool((d <= chunks[:, k, 3] + 1e-6).all())
+    # binning is a permutation of the samples
+    idx = world[..., 7].contiguous().view(torch.int32).sort(dim=1).values
+    assert bool((idx == torch.arange(300, device=idx.device, dtype=torch.int32)[None]).all())
+    # and the patches are compact: mean chunk radius well below the facet radius
+    assert float(chunks[..., 3].mean()) < 0.6 * float(bounds[:, 3].mean())
+
+
 def test_response_matrix_rows_are_single_source_images():
     """BASELINE config 4 geometry: CT3 + roughness 24", parallel grid; row i == render of source i."""
     tel = _tel("CT3", 16, step=4, seed=42).apply_roughness(24)
