@@ -217,7 +217,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             PixCache cache;
             cache.reset();
             // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
-            const bool sub_beams = cull && sc.chunk_bounds != nullptr && n_list > 0 && n_list <= 32;
+            const bool sub_beams = cull && sc.chunk_bounds != nullptr && n_list >= 2 && n_list <= 32;   // one candidate: the test costs what it saves
             const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
             for (int mb = m0; mb < m1; mb += 32) {
                 const int m = mb + lane;
@@ -240,8 +240,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                     d = src;
                 }
                 // render.py:138 shadow of the incoming leg (infinite ray back towards the source)
-                const bool blocked = sub_beams ? occluded_masked(ob, o, -d, list, n_list_cyl, sub_mask)
-                                               : occluded(ob, o, -d, list, n_list_cyl, n_list);
+                const bool blocked = occluded(ob, o, -d, list, n_list_cyl, n_list, sub_mask);
                 // render.py:140-141, reflection.py:17-19
                 const float c = dot(d, n);
                 d = d - (2.0f * c) * n;

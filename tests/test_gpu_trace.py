@@ -69,7 +69,7 @@ def _compare_image(img, r, shape, rtol=1e-4):
     np.testing.assert_allclose(got[clean], oimg[clean], rtol=rtol, atol=1e-7 * max(oimg.max(), 1e-30))
     # and the image must equal the binning of the kernel's own per-ray output everywhere
     own = np.bincount(r["pix"][r["pix"] >= 0], weights=r["v"][r["pix"] >= 0].astype(np.float64), minlength=npx)
-    np.testing.assert_allclose(got, own, rtol=2e-5, atol=1e-7 * max(own.max(), 1e-30))
+    np.testing.assert_allclose(got, own, rtol=5e-5, atol=1e-7 * max(own.max(), 1e-30))
     return oimg
 
 
