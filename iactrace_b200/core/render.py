@@ -35,7 +35,8 @@ def _world_tables(tel, stage0):
     for g in stage0:
         srcs += [g.positions, g.rotations, g.perturbation_scale, g.points, g.normals, g.perturbation_delta, g.weights]
     M0 = stage0[0].points.shape[1]
-    binned = bool(config.bin_samples_min) and M0 >= config.bin_samples_min
+    binned = (bool(config.bin_samples_min) and M0 >= config.bin_samples_min
+              and sum(len(g) for g in (tel.obstruction_groups or [])) >= config.bin_obstructions_min)
     sig = (_tensor_sig(srcs), binned)
     hit = tel._cache.get("world")
     if hit is not None and hit[0] == sig:

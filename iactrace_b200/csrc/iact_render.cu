@@ -162,7 +162,7 @@ struct PixCache {
 #ifndef IACT_MIN_BLOCKS
 #define IACT_MIN_BLOCKS 4
 #endif
-template <int SRC, int SENS, int MODE, bool STAGES>
+template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
 __global__ void __launch_bounds__(256, STAGES ? 2 : IACT_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
              const LaunchPlan plan, const FacetLists fl, float* __restrict__ out, float* __restrict__ out_val,
@@ -217,7 +217,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             PixCache cache;
             cache.reset();
             // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
-            const bool sub_beams = cull && sc.chunk_bounds != nullptr && n_list >= 2 && n_list <= 32;   // one candidate: the test costs what it saves
+            const bool sub_beams = SUB && cull && n_list >= 2 && n_list <= 32;   // one candidate: the test costs what it saves
             const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
             for (int mb = m0; mb < m1; mb += 32) {
                 const int m = mb + lane;
@@ -225,7 +225,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 const int mm = live ? m : m1 - 1;
                 const float4 a = __ldg(tab + 2 * mm), b = __ldg(tab + 2 * mm + 1);
                 unsigned sub_mask = 0xffffffffu;
-                if (sub_beams) {
+                if (SUB && sub_beams) {
                     const Beam cb = make_beam<SRC>(__ldg(cbs + (mb >> 5)), src);
                     sub_mask = __ballot_sync(0xffffffffu, lane < n_list && (!cb.ok || keep_primitive(ob, cb, list[lane])));
                 }
@@ -240,7 +240,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                     d = src;
                 }
                 // render.py:138 shadow of the incoming leg (infinite ray back towards the source)
-                const bool blocked = occluded(ob, o, -d, list, n_list_cyl, n_list, sub_mask);
+                const bool blocked = occluded<SUB>(ob, o, -d, list, n_list_cyl, n_list, sub_mask);
                 // render.py:140-141, reflection.py:17-19
                 const float c = dot(d, n);
                 d = d - (2.0f * c) * n;
@@ -343,13 +343,10 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const SensDev se, const
     }
 }
 
-template <int SRC, int SENS, int MODE, bool STAGES>
-int launch_variant(const SceneDev& d, const float* sources, const float* values, const LaunchPlan& plan, const FacetLists& fl,
-                   float* out, float* out_val, int* out_pix, cudaStream_t stream) {
+template <typename K>
+int launch_kernel(K kern, const SceneDev& d, const float* sources, const float* values, const LaunchPlan& plan, const FacetLists& fl,
+                  float* out, float* out_val, int* out_pix, cudaStream_t stream, size_t smem) {
     const int threads = 256;
-    const size_t smem = smem_bytes(d, SENS, MODE, threads / 32);
-    if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
-    auto kern = trace_kernel<SRC, SENS, MODE, STAGES>;
     if (smem > 48 * 1024) IACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     IACT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -359,6 +356,16 @@ int launch_variant(const SceneDev& d, const float* sources, const float* values,
     kern<<<grid, threads, smem, stream>>>(d, sources, values, plan, fl, out, out_val, out_pix);
     iact_count_launch();
     return iact_check_cuda(cudaGetLastError(), "trace_kernel launch");
+}
+
+template <int SRC, int SENS, int MODE, bool STAGES>
+int launch_variant(const SceneDev& d, const float* sources, const float* values, const LaunchPlan& plan, const FacetLists& fl,
+                   float* out, float* out_val, int* out_pix, cudaStream_t stream) {
+    const int threads = 256;
+    const size_t smem = smem_bytes(d, SENS, MODE, threads / 32);
+    if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
+    if (d.chunk_bounds && !STAGES) return launch_kernel(trace_kernel<SRC, SENS, MODE, STAGES, true>, d, sources, values, plan, fl, out, out_val, out_pix, stream, smem);
+    return launch_kernel(trace_kernel<SRC, SENS, MODE, STAGES, false>, d, sources, values, plan, fl, out, out_val, out_pix, stream, smem);
 }
 
 #define ARGS const SceneDev& d, const float* a, const float* b, const LaunchPlan& p, const FacetLists& fl, float* o, float* ov, int* op, cudaStream_t st

@@ -180,13 +180,13 @@ def test_binned_table_and_sub_beam_culling_are_exact():
         val = np.linspace(0.5, 1.5, len(src)).astype(np.float32)
         out = {}
         for name, cull, bin_min in (("binned+culled", True, 256), ("binned brute force", False, 256), ("plain+culled", True, 0)):
-            Rm.cull_obstructions, Rm.bin_samples_min = cull, bin_min
+            Rm.cull_obstructions, Rm.bin_samples_min, Rm.bin_obstructions_min = cull, bin_min, 1
             try:
                 xy, v, pix = render_debug(tel, src, val, stype, 0, return_pixels=True)
                 img = render(tel, src, val, stype, 0)
                 out[name] = (xy.cpu().numpy(), v.cpu().numpy(), pix.cpu().numpy(), img.cpu().numpy())
             finally:
-                Rm.cull_obstructions, Rm.bin_samples_min = True, 256
+                Rm.cull_obstructions, Rm.bin_samples_min, Rm.bin_obstructions_min = True, 256, 100
         ref = out["plain+culled"]
         for name in ("binned+culled", "binned brute force"):
             for a, b in zip(out[name][:3], ref[:3]):
