@@ -309,7 +309,9 @@ def main():
         N.check(N.lib().iact_cull_stats(sc, N.ptr(src_dev), len(src_np), 0 if stype == "point" else 1,
                                         stats.data_ptr(), None))
         torch.cuda.synchronize()
-        n_cyl_kept, n_oth_kept, n_pairs, n_lvl1 = [int(x) for x in stats.tolist()]
+        n_cyl_kept, n_oth_kept, n_rays_stat, n_lvl1 = [int(x) for x in stats.tolist()]
+        n_pairs = max(n_rays_stat, 1)                  # per-ray averages
+        n_lvl1 = n_lvl1 * w["M"]
         sensor_kind = "hex" if hasattr(tel.sensors[w["sensor"]], "hex_size") else "square"
         n_cyl = sc.n_cyl
         n_oth = sc.n_box + sc.n_sph + sc.n_obox + sc.n_tri

@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(256) cull_stats_kernel(const __grid_constant__
     __syncthreads();
     unsigned long long a = 0, b = 0, c = 0, l1 = 0;
     const long long n_pairs = (long long)sc.F * S;
+    const int M = sc.M, n_chunks = (M + 31) >> 5;
     for (long long i = (long long)blockIdx.x * nwarps + warp; i < n_pairs; i += (long long)gridDim.x * nwarps) {
         const int f = (int)(i / S), s = (int)(i - (long long)f * S);
         const V3 src = v3(sources[3 * s], sources[3 * s + 1], sources[3 * s + 2]);
@@ -323,7 +324,19 @@ __global__ void __launch_bounds__(256) cull_stats_kernel(const __grid_constant__
         int ncyl = 0, n;
         if (cnt.x >= 0) n = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, ncyl);
         else            n = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, ncyl);
-        a += ncyl; b += n - ncyl; c += 1; l1 += cnt.x >= 0 ? cnt.y : n_obs;
+        if (sc.chunk_bounds && n >= 2 && n <= 32) {
+            // level 3: what each 32-row run actually tests (same rule as trace_kernel<..., SUB = true>)
+            for (int k = 0; k < n_chunks; ++k) {
+                const Beam cb = make_beam<SRC>(__ldg(sc.chunk_bounds + (size_t)f * n_chunks + k), src);
+                const unsigned mask = __ballot_sync(0xffffffffu, lane < n && (!cb.ok || keep_primitive(ob, cb, list[lane])));
+                const unsigned mc = mask & ((1u << ncyl) - 1u);
+                const int rays = min(32, M - 32 * k);
+                a += (unsigned long long)__popc(mc) * rays; b += (unsigned long long)__popc(mask & ~mc) * rays;
+            }
+        } else {
+            a += (unsigned long long)ncyl * M; b += (unsigned long long)(n - ncyl) * M;
+        }
+        c += M; l1 += cnt.x >= 0 ? cnt.y : n_obs;
         __syncwarp();
     }
     if (lane == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); atomicAdd(out + 2, c); atomicAdd(out + 3, l1); }

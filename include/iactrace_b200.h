@@ -205,8 +205,8 @@ int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
                     const float* cotangent, const IactGrads* grads, void* stream);
 
 /* Diagnostics for the roofline: candidate-list lengths of the conservative obstruction culling,
- * summed over all (facet, source) pairs.  out4: device uint64[4] = {sum cylinders kept,
- * sum other primitives kept, number of pairs, sum of the facet-level (level-1) list lengths}. */
+ * over all rays.  out4: device uint64[4] = {cylinder tests executed (summed over rays), tests of other
+ * primitives, number of rays, sum over (facet, source) pairs of the facet-level (level-1) list length}. */
 int iact_cull_stats(const IactScene* scene, const float* sources, int n_sources, int source_type,
                     unsigned long long* out4, void* stream);
 
