@@ -125,6 +125,76 @@ __device__ __forceinline__ void splat_soft_hex_warp(const SensDev& se, const LUT
         }
 }
 
+// Soft hex splat with one ring of neighbours (7 taps), cached per warp item: the rays of one
+// (facet, source) pair almost always share their base hexagon, so each lane keeps 7 per-tap partial sums
+// for the warp's first base hexagon in registers and the shared histogram is touched 7 times per item.
+// Rays with another base hexagon take the per-tap warp-aggregated path.
+struct SoftHexCache {
+    float qb0, rb0; bool set;
+    float acc[7];
+    __device__ __forceinline__ void reset() { set = false; qb0 = rb0 = 0.f; for (int i = 0; i < 7; ++i) acc[i] = 0.f; }
+    // tap order: the 7 (oq, orr) pairs with max(|oq|, |orr|, |oq + orr|) <= 1, oq outer, orr inner
+    template <typename LUT>
+    __device__ __forceinline__ void add(const SensDev& se, const LUT* lut, bool active, float x, float y, float val, float* hist) {
+        float xg, yg; hex_grid_coords(se, x, y, xg, yg);
+        const float q = se.ax_qx * xg - se.ax_qy * yg, r = se.ax_ry * yg;
+        float qb, rb; hex_round(q, r, qb, rb);
+        active = active && (fabsf(qb) < 1e6f) && (fabsf(rb) < 1e6f);
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        if (am == 0u) return;
+        if (!set) {
+            const int leader = __ffs(am) - 1;
+            qb0 = __shfl_sync(0xffffffffu, qb, leader); rb0 = __shfl_sync(0xffffffffu, rb, leader);
+            set = true;
+        }
+        const float ddx = xg - se.size_sqrt3 * (qb + rb * 0.5f), ddy = yg - se.size_1p5 * rb;
+        const float inv_sigma = 1.0f / se.sigma;
+        float w[7], wsum = 0.f;
+        int t = 0;
+#pragma unroll
+        for (int oq = -1; oq <= 1; ++oq)
+#pragma unroll
+            for (int orr = -1; orr <= 1; ++orr) {
+                if (oq + orr < -1 || oq + orr > 1) continue;
+                const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
+                const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
+                const float z = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) * se.inv_inradius * inv_sigma;
+                w[t] = expf(-0.5f * z * z); wsum += w[t]; ++t;
+            }
+        const float scale = active ? val / wsum : 0.f;
+        const bool cached = active && qb == qb0 && rb == rb0;
+        if (cached) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) acc[i] += scale * w[i];
+        }
+        if (__any_sync(0xffffffffu, active && !cached)) {           // rare: a second base hexagon in this item
+            t = 0;
+            for (int oq = -1; oq <= 1; ++oq)
+                for (int orr = -1; orr <= 1; ++orr) {
+                    if (oq + orr < -1 || oq + orr > 1) continue;
+                    const int pix = (active && !cached) ? hex_lookup(se, lut, qb + (float)oq, rb + (float)orr) : -1;
+                    warp_hist_add(hist, pix, scale * w[t]); ++t;
+                }
+        }
+    }
+    template <typename LUT>
+    __device__ __forceinline__ void flush(const SensDev& se, const LUT* lut, float* hist) {
+        if (!set) return;
+        const unsigned lane = threadIdx.x & 31u;
+        int t = 0;
+        for (int oq = -1; oq <= 1; ++oq)
+            for (int orr = -1; orr <= 1; ++orr) {
+                if (oq + orr < -1 || oq + orr > 1) continue;
+                float v = acc[t]; ++t;
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0 && v != 0.f) {
+                    const int pix = hex_lookup(se, lut, qb0 + (float)oq, rb0 + (float)orr);
+                    if (pix >= 0) atomicAdd(hist + pix, v);
+                }
+            }
+    }
+};
+
 // Per-warp-item pixel cache: the rays of one (facet, source) pair land in 1-3 hex pixels, so the warp
 // keeps up to three (pixel, per-lane partial sum) slots in registers across all its iterations and
 // touches the shared histogram once per slot at the end of the item; rays outside the three cached
@@ -216,6 +286,9 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             const float4* tab = sc.world + ((size_t)f * M) * 2;
             PixCache cache;
             cache.reset();
+            SoftHexCache scache;
+            const bool soft7 = SENS == SENS_HEX && MODE != MODE_DEBUG && soft && sc.sens.ksize == 1;
+            if (soft7) scache.reset();
             // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
             const bool sub_beams = SUB && cull && n_list >= 2 && n_list <= 32;   // one candidate: the test costs what it saves
             const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
@@ -268,7 +341,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 } else {
                     const bool add = live && val != 0.f;
                     if (SENS == SENS_HEX) {
-                        if (soft) splat_soft_hex_warp(sc.sens, lut, add, x, y, val, hist);
+                        if (soft7) scache.add(sc.sens, lut, add, x, y, val, hist);
+                        else if (soft) splat_soft_hex_warp(sc.sens, lut, add, x, y, val, hist);
                         else cache.add(hist, add ? hex_pixel(sc.sens, lut, x, y) : -1, val);
                     } else if (add) {
                         if (soft) splat_soft_square(sc.sens, x, y, val, gout);
@@ -277,6 +351,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 }
             }
             if (SENS == SENS_HEX && MODE != MODE_DEBUG && !soft) cache.flush(hist);
+            if (soft7) scache.flush(sc.sens, lut, hist);
             __syncwarp();
         }
         if (MODE == MODE_MATRIX && SENS == SENS_HEX) {
