@@ -8,7 +8,7 @@
 namespace {
 
 enum { MODE_RENDER = 0, MODE_MATRIX = 1, MODE_DEBUG = 2 };
-enum { SENS_SQUARE = 0, SENS_HEX = 1 };
+enum { SENS_SQUARE = 0, SENS_HEX = 1, SENS_SOFT_HEX = 2 };   // hard/soft square share one instantiation
 
 struct LaunchPlan {
     int S, n_chunks, chunk_facets, msplit, msize;
@@ -238,7 +238,7 @@ size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
     const int n_obs = d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri;
     size_t fl = obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, d.cull != 0);
     fl += stage_floats(d);
-    if (sens == SENS_HEX) {
+    if (sens != SENS_SQUARE) {
         if (mode != MODE_DEBUG) fl += d.sens.npix;
         fl += (d.sens.tq * d.sens.tr + 1) / 2;
     }

@@ -247,7 +247,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     if (STAGES) { stage_mirrors(sc, p); p += stage_floats(sc); }
     float* hist = nullptr;
     const short* lut = nullptr;
-    if (SENS == SENS_HEX) {
+    if (SENS != SENS_SQUARE) {
         if (MODE != MODE_DEBUG) { hist = p; p += sc.sens.npix; }
         short* l = reinterpret_cast<short*>(p);
         for (int i = threadIdx.x; i < sc.sens.tq * sc.sens.tr; i += blockDim.x) l[i] = (short)sc.sens.lookup[i];
@@ -260,8 +260,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     __syncthreads();
 
     const int M = sc.M;
-    const bool soft = sc.sens.kind >= IACT_SENSOR_SOFT_SQUARE;
-    const size_t npix = SENS == SENS_HEX ? (size_t)sc.sens.npix : (size_t)sc.sens.W * sc.sens.H;
+    const bool soft = SENS == SENS_SQUARE ? sc.sens.kind == IACT_SENSOR_SOFT_SQUARE : SENS == SENS_SOFT_HEX;
+    const size_t npix = SENS != SENS_SQUARE ? (size_t)sc.sens.npix : (size_t)sc.sens.W * sc.sens.H;
 
     for (long long item = blockIdx.x; item < plan.n_items; item += gridDim.x) {
         const int s = (int)(item / plan.n_chunks), ch = (int)(item - (long long)s * plan.n_chunks);
@@ -287,7 +287,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             PixCache cache;
             cache.reset();
             SoftHexCache scache;
-            const bool soft7 = SENS == SENS_HEX && MODE != MODE_DEBUG && soft && sc.sens.ksize == 1;
+            const bool soft7 = SENS == SENS_SOFT_HEX && MODE != MODE_DEBUG && sc.sens.ksize == 1;
             if (soft7) scache.reset();
             // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
             const bool sub_beams = SUB && cull && n_list >= 2 && n_list <= 32;   // one candidate: the test costs what it saves
@@ -334,27 +334,28 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                         out[2 * ri] = x; out[2 * ri + 1] = y; out_val[ri] = val;
                         if (out_pix) {
                             int pix = -1;
-                            if (!soft) pix = SENS == SENS_HEX ? hex_pixel(sc.sens, lut, x, y) : square_pixel(sc.sens, x, y);
+                            if (!soft) pix = SENS != SENS_SQUARE ? hex_pixel(sc.sens, lut, x, y) : square_pixel(sc.sens, x, y);
                             out_pix[ri] = pix;
                         }
                     }
                 } else {
                     const bool add = live && val != 0.f;
-                    if (SENS == SENS_HEX) {
+                    if (SENS == SENS_SOFT_HEX) {
                         if (soft7) scache.add(sc.sens, lut, add, x, y, val, hist);
-                        else if (soft) splat_soft_hex_warp(sc.sens, lut, add, x, y, val, hist);
-                        else cache.add(hist, add ? hex_pixel(sc.sens, lut, x, y) : -1, val);
+                        else splat_soft_hex_warp(sc.sens, lut, add, x, y, val, hist);
+                    } else if (SENS == SENS_HEX) {
+                        cache.add(hist, add ? hex_pixel(sc.sens, lut, x, y) : -1, val);
                     } else if (add) {
                         if (soft) splat_soft_square(sc.sens, x, y, val, gout);
                         else { const int pix = square_pixel(sc.sens, x, y); if (pix >= 0) atomicAdd(gout + pix, val); }
                     }
                 }
             }
-            if (SENS == SENS_HEX && MODE != MODE_DEBUG && !soft) cache.flush(hist);
-            if (soft7) scache.flush(sc.sens, lut, hist);
+            if (SENS == SENS_HEX && MODE != MODE_DEBUG) cache.flush(hist);
+            if (SENS == SENS_SOFT_HEX && soft7) scache.flush(sc.sens, lut, hist);
             __syncwarp();
         }
-        if (MODE == MODE_MATRIX && SENS == SENS_HEX) {
+        if (MODE == MODE_MATRIX && SENS != SENS_SQUARE) {
             __syncthreads();
             if (plan.n_chunks == 1) {
                 for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) { gout[i] = hist[i]; hist[i] = 0.f; }
@@ -367,7 +368,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             __syncthreads();
         }
     }
-    if (MODE == MODE_RENDER && SENS == SENS_HEX) {
+    if (MODE == MODE_RENDER && SENS != SENS_SQUARE) {
         __syncthreads();
         for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) {
             const float v = hist[i];
@@ -464,8 +465,9 @@ int launch_stages(ARGS) {
 }
 template <int SRC, int MODE>
 int launch_sens(ARGS) {
-    const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
-    return hex ? launch_stages<SRC, SENS_HEX, MODE>(PASS) : launch_stages<SRC, SENS_SQUARE, MODE>(PASS);
+    if (d.sens.kind == IACT_SENSOR_HEX) return launch_stages<SRC, SENS_HEX, MODE>(PASS);
+    if (d.sens.kind == IACT_SENSOR_SOFT_HEX) return launch_stages<SRC, SENS_SOFT_HEX, MODE>(PASS);
+    return launch_stages<SRC, SENS_SQUARE, MODE>(PASS);
 }
 template <int MODE>
 int launch_src(int source_type, ARGS) {
