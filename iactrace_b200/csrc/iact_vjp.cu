@@ -72,27 +72,31 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
     const int K = se.ksize;
     const float inv_sigma = 1.0f / se.sigma;
     float D = 0.f, Nn = 0.f, gx = 0.f, gy = 0.f, wx = 0.f, wy = 0.f;
-    for (int oq = -K; oq <= K; ++oq)
-        for (int orr = -K; orr <= K; ++orr) {
-            if (max(max(abs(oq), abs(orr)), abs(oq + orr)) > K) continue;
-            const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
-            const float a = ddx - ox, b = ddy - oy;
-            const float aa = fabsf(a), ab = fabsf(b);
-            const float alt = 0.5f * aa + 0.8660254037844386f * ab;
-            const bool first = aa >= alt;
-            const float hd = fmaxf(aa, alt) * se.inv_inradius;
-            const float z = hd * inv_sigma;
-            const float w = expf(-0.5f * z * z);
-            // d hd / d a, d hd / d b  (sign(0) = 0, as jnp.abs)
-            const float sa = a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f), sb = b > 0.f ? 1.f : (b < 0.f ? -1.f : 0.f);
-            const float dha = (first ? sa : 0.5f * sa) * se.inv_inradius;
-            const float dhb = (first ? 0.f : 0.8660254037844386f * sb) * se.inv_inradius;
-            const float k = -w * z * inv_sigma;                 // dw/dhd
-            const float dwx = k * dha, dwy = k * dhb;
-            const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
-            const float g = pix >= 0 ? __ldg(G + pix) : 0.f;
-            D += w; Nn += g * w; gx += g * dwx; gy += g * dwy; wx += dwx; wy += dwy;
-        }
+    auto tap = [&](int oq, int orr) {
+        const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
+        const float a = ddx - ox, b = ddy - oy;
+        const float aa = fabsf(a), ab = fabsf(b);
+        const float alt = 0.5f * aa + 0.8660254037844386f * ab;
+        const bool first = aa >= alt;
+        const float z = fmaxf(aa, alt) * se.inv_inradius * inv_sigma;
+        const float w = expf(-0.5f * z * z);
+        // d hd / d a, d hd / d b  (sign(0) = 0, as jnp.abs)
+        const float sa = a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f), sb = b > 0.f ? 1.f : (b < 0.f ? -1.f : 0.f);
+        const float dha = (first ? sa : 0.5f * sa) * se.inv_inradius;
+        const float dhb = (first ? 0.f : 0.8660254037844386f * sb) * se.inv_inradius;
+        const float k = -w * z * inv_sigma;                 // dw/dhd
+        const float dwx = k * dha, dwy = k * dhb;
+        const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
+        const float g = pix >= 0 ? __ldg(G + pix) : 0.f;
+        D += w; Nn += g * w; gx += g * dwx; gy += g * dwy; wx += dwx; wy += dwy;
+    };
+    if (K == 1) {                                           // the common 7-tap case, fully unrolled
+        tap(-1, 0); tap(-1, 1); tap(0, -1); tap(0, 0); tap(0, 1); tap(1, -1); tap(1, 0);
+    } else {
+        for (int oq = -K; oq <= K; ++oq)
+            for (int orr = -K; orr <= K; ++orr)
+                if (max(max(abs(oq), abs(orr)), abs(oq + orr)) <= K) tap(oq, orr);
+    }
     const float invD = 1.0f / D;
     dval = Nn * invD;
     const float dxg = (gx - dval * wx) * invD, dyg = (gy - dval * wy) * invD;
