@@ -211,6 +211,51 @@ def test_binned_table_and_sub_beam_culling_are_exact():
     assert float(chunks[..., 3].mean()) < 0.6 * float(bounds[:, 3].mean())
 
 
+def test_long_candidate_lists_and_table_limits():
+    """More than 32 candidates per beam (per-run culling steps aside), single ray, and the documented
+    shared-memory limit for huge obstruction tables."""
+    from iactrace_b200.core import Cylinder, Sphere, group_obstructions
+    rng = np.random.default_rng(7)
+    base = _tel("CT5", 320, n_mirrors=6, step=100)
+    c = base.mirror_groups[0].positions.cpu().numpy()
+    obs = []
+    for k in range(60):                                  # a thicket of thin rods right above every facet
+        f = k % len(c)
+        a = c[f] + np.array([rng.uniform(-0.6, 0.6), rng.uniform(-0.6, 0.6), rng.uniform(2.0, 6.0)])
+        obs.append(Cylinder(a, a + np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), 0.05]), 0.004))
+    tel = I.Telescope(base.mirror_groups, group_obstructions(obs), base.sensors)
+    src = point_grid(2, 0.5)
+    val = np.ones(4, np.float32)
+    res = []
+    for cull, obs_min in ((True, 1), (False, 1), (True, 10 ** 6)):
+        Rm.cull_obstructions, Rm.bin_obstructions_min = cull, obs_min
+        try:
+            xy, v = render_debug(tel, src, val, "point", 0)
+            res.append((xy.cpu().numpy(), v.cpu().numpy()))
+        finally:
+            Rm.cull_obstructions, Rm.bin_obstructions_min = True, 100
+    for r in res[1:]:
+        assert np.array_equal(r[1], res[0][1]) and np.array_equal(r[0], res[0][0])
+    assert 0.005 < (res[0][1] == 0).mean() < 0.5
+    # one facet, one sample, one source
+    one = I.Telescope([base.mirror_groups[0]], [], base.sensors)
+    from iactrace_b200._util import replace
+    g = one.mirror_groups[0]
+    g1 = replace(g, positions=g.positions[:1], rotations=g.rotations[:1], perturbation_scale=g.perturbation_scale[:1],
+                 points=g.points[:1, :1].contiguous(), normals=g.normals[:1, :1].contiguous(),
+                 perturbation_delta=g.perturbation_delta[:1, :1].contiguous(), weights=g.weights[:1, :1].contiguous(),
+                 vertices=g.vertices[:1], offsets=g.offsets[:1])
+    tiny = replace(one, mirror_groups=[g1])
+    xy, v = render_debug(tiny, src[:1], val[:1], "point", 0)
+    assert xy.shape == (1, 2) and float(v[0]) > 0
+    assert abs(float(render(tiny, src[:1], val[:1], "point", 0).sum()) - float(v[0])) < 1e-6 * float(v[0]) + 1e-12
+    # obstruction tables beyond the shared-memory budget are refused, not silently mishandled
+    big = I.Telescope(base.mirror_groups, group_obstructions([Sphere(rng.uniform(-5, 5, 3) + [0, 0, 20], 0.01) for _ in range(7000)]),
+                      base.sensors)
+    with pytest.raises(NotImplementedError, match="shared memory"):
+        render(big, src, val, "point", 0)
+
+
 def test_response_matrix_rows_are_single_source_images():
     """BASELINE config 4 geometry: CT3 + roughness 24", parallel grid; row i == render of source i."""
     tel = _tel("CT3", 16, step=4, seed=42).apply_roughness(24)
