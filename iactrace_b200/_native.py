@@ -8,7 +8,11 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libiactrace_b200.so"
+import os
+
+# IACTRACE_B200_LIB selects another build of the same library (kernel tuning experiments); there is
+# still no fallback: a missing file raises.
+_LIB_PATH = Path(os.environ.get("IACTRACE_B200_LIB") or Path(__file__).resolve().parent / "csrc" / "libiactrace_b200.so")
 _lib = None
 
 MAX_ASPH = 8

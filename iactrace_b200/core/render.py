@@ -29,14 +29,17 @@ def _tensor_sig(ts):
     return tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in ts)
 
 
-def _world_tables(tel, stage0):
+def _world_tables(tel, stage0, later_stages=False):
     """Packed world-frame sample table (F,M,8) + facet bounding spheres, cached on the Telescope."""
     srcs = []
     for g in stage0:
         srcs += [g.positions, g.rotations, g.perturbation_scale, g.points, g.normals, g.perturbation_delta, g.weights]
     M0 = stage0[0].points.shape[1]
+    n_obs = sum(len(g) for g in (tel.obstruction_groups or []))
+    # with optical stages >= 1 the leg towards the next mirror is culled per 32-ray run from the rays
+    # themselves (occluded_leg_culled), which needs spatially compact runs whatever the primitive count
     binned = (bool(config.bin_samples_min) and M0 >= config.bin_samples_min
-              and sum(len(g) for g in (tel.obstruction_groups or [])) >= config.bin_obstructions_min)
+              and (n_obs >= config.bin_obstructions_min or (later_stages and n_obs >= 1)))
     sig = (_tensor_sig(srcs), binned)
     hit = tel._cache.get("world")
     if hit is not None and hit[0] == sig:
@@ -127,7 +130,7 @@ def build_scene(tel, sensor_idx: int, keep: list, cull: bool | None = None):
     if not stages or 0 not in stages:
         return None, sensor
     sc = N.IactScene()
-    world, bounds, chunks = _world_tables(tel, stages[0])
+    world, bounds, chunks = _world_tables(tel, stages[0], later_stages=len(stages) > 1)
     keep += [world, bounds, chunks]
     sc.n_facets, sc.n_samples = world.shape[0], world.shape[1]
     sc.world, sc.bounds, sc.chunk_bounds = N.ptr(world), N.ptr(bounds), N.ptr(chunks)

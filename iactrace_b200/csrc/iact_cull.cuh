@@ -95,6 +95,47 @@ __device__ __forceinline__ int build_list(const ObsSmem& ob, const Beam& b, cons
     return n;
 }
 
+// _check_occlusions for the leg towards an optical stage >= 1 (render.py:76), culled per warp from the
+// rays themselves: origins lie within R of the leader lane's origin and directions within `spread`
+// (chord) of the leader's, so a primitive that beam cannot reach is skipped for all 32 rays.  Exact for
+// the same reason as the beam culling of the incoming leg; wide bundles (unsorted samples on a strongly
+// curved facet) fall back to testing everything.  `need` = this lane's result matters (rays already at
+// value 0 stay 0 whatever the test says).  Must be called by all 32 lanes; needs the culling proxies.
+__device__ __forceinline__ bool occluded_leg_culled(const ObsSmem& ob, V3 o, V3 d, bool need) {
+    const unsigned am = __ballot_sync(0xffffffffu, need);
+    if (am == 0u) return false;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(am) - 1;
+    Beam b;
+    b.c = v3(__shfl_sync(0xffffffffu, o.x, leader), __shfl_sync(0xffffffffu, o.y, leader), __shfl_sync(0xffffffffu, o.z, leader));
+    b.u = v3(__shfl_sync(0xffffffffu, d.x, leader), __shfl_sync(0xffffffffu, d.y, leader), __shfl_sync(0xffffffffu, d.z, leader));
+    const V3 eo = o - b.c, ed = d - b.u;
+    // non-negative floats order like their bit patterns; a NaN has the largest pattern and switches culling off
+    const float r2 = __uint_as_float(__reduce_max_sync(0xffffffffu, need ? __float_as_uint(dot(eo, eo)) : 0u));
+    const float s2 = __uint_as_float(__reduce_max_sync(0xffffffffu, need ? __float_as_uint(dot(ed, ed)) : 0u));
+    b.R = sqrtf(r2) * 1.001f + 1e-6f;
+    b.spread = sqrtf(s2) * 1.001f + 1e-6f;
+    b.invD = 0.f;
+    const float u2 = dot(b.u, b.u);
+    b.ok = (b.spread < 0.15f) && (b.R < 1e6f) && (u2 > 0.99f) && (u2 < 1.01f);
+    const int n_obs = ob.n_cyl + ob.n_rest;
+    bool blocked = false;
+    if (!b.ok) {
+        if (need) blocked = occluded(ob, o, d, nullptr, 0, 0);
+        return blocked;
+    }
+    for (int base = 0; base < n_obs; base += 32) {
+        const int id = base + (int)lane;
+        unsigned mask = __ballot_sync(0xffffffffu, id < n_obs && keep_primitive(ob, b, id));
+        while (mask) {
+            const int e = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            if (need) blocked |= hit_primitive(ob, base + e, o, d);
+        }
+    }
+    return blocked;
+}
+
 // ---------------------------------------------------------------- level-1 culling: facet x all sources
 // One warp per facet: bounding cone of the directions towards all sources, then one pass over the
 // primitives.  Writes ids[f*stride ..] and count[f] = (n_cyl_kept, n_total_kept) or (-1,-1).

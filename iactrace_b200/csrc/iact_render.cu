@@ -232,8 +232,11 @@ struct PixCache {
 #ifndef IACT_MIN_BLOCKS
 #define IACT_MIN_BLOCKS 4
 #endif
+#ifndef IACT_MIN_BLOCKS_STAGES
+#define IACT_MIN_BLOCKS_STAGES 2
+#endif
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
-__global__ void __launch_bounds__(256, STAGES ? 2 : IACT_MIN_BLOCKS)
+__global__ void __launch_bounds__(256, STAGES ? IACT_MIN_BLOCKS_STAGES : IACT_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
              const LaunchPlan plan, const FacetLists fl, float* __restrict__ out, float* __restrict__ out_val,
              int* __restrict__ out_pix) {
@@ -321,7 +324,9 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 if (STAGES) {
                     const float* rec = stage_rec;
                     for (int st = 0; st < sc.n_stages; ++st) {
-                        reflect_at_stage(sc.stages[st].n, rec, sc.stages[st].verts, ob, o, d, val);
+                        const bool leg_blocked = cull ? occluded_leg_culled(ob, o, d, val != 0.f)
+                                                      : occluded(ob, o, d, nullptr, 0, 0);
+                        reflect_at_stage(sc.stages[st].n, rec, sc.stages[st].verts, leg_blocked, !cull, o, d, val);
                         rec += (size_t)sc.stages[st].n * STAGE_REC;
                     }
                 }
@@ -453,7 +458,7 @@ int launch_variant(const SceneDev& d, const float* sources, const float* values,
     const int threads = 256;
     const size_t smem = smem_bytes(d, SENS, MODE, threads / 32);
     if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
-    if (d.chunk_bounds && !STAGES) return launch_kernel(trace_kernel<SRC, SENS, MODE, STAGES, true>, d, sources, values, plan, fl, out, out_val, out_pix, stream, smem);
+    if (d.chunk_bounds) return launch_kernel(trace_kernel<SRC, SENS, MODE, STAGES, true>, d, sources, values, plan, fl, out, out_val, out_pix, stream, smem);
     return launch_kernel(trace_kernel<SRC, SENS, MODE, STAGES, false>, d, sources, values, plan, fl, out, out_val, out_pix, stream, smem);
 }
 

@@ -110,7 +110,7 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
 // ---------------------------------------------------------------- optical stages >= 1
 // Forward selection of the mirror a ray hits in one stage (same arithmetic as reflect_at_stage, plus
 // the index and ray parameter needed by the backward pass).
-__device__ __forceinline__ bool stage_select(int n_mirrors, const float* rec, const float* verts, V3 o, V3 d,
+__device__ __forceinline__ bool stage_select(int n_mirrors, const float* rec, const float* verts, bool full_scan, V3 o, V3 d,
                                              int& best_mi, float& best_t) {
     best_t = INFINITY; best_mi = -1;
     for (int mi = 0; mi < n_mirrors; ++mi) {
@@ -120,7 +120,7 @@ __device__ __forceinline__ bool stage_select(int n_mirrors, const float* rec, co
 #pragma unroll
         for (int k = 0; k < 9; ++k) R.m[k] = r[24 + k];
         SurfRef s;
-        s.c = r[8]; s.k = r[9]; s.kc2 = r[33]; s.n_asph = (int)r[10]; s.asph = r + 11;
+        s.c = r[8]; s.k = r[9]; s.kc2 = r[33]; s.n_asph = (int)r[10]; s.asph = r + 11; s.full_scan = full_scan;
         V3 pl, nl;
         float t = surface_intersect(s, r[6], r[7], mulT(R, o - pos), mulT(R, d), pl, nl);
         bool inside;
@@ -152,7 +152,7 @@ __device__ __forceinline__ StageGeom stage_geometry(const float* r, V3 o, V3 d, 
 #pragma unroll
     for (int k = 0; k < 9; ++k) g.R.m[k] = r[24 + k];
     SurfRef s;
-    s.c = r[8]; s.k = r[9]; s.kc2 = r[33]; s.n_asph = (int)r[10]; s.asph = r + 11;
+    s.c = r[8]; s.k = r[9]; s.kc2 = r[33]; s.n_asph = (int)r[10]; s.asph = r + 11; s.full_scan = false;
     g.ol = mulT(g.R, o - g.pos); g.dl = mulT(g.R, d);
     const float x0 = r[6], y0 = r[7];
     const float x = g.ol.x + t * g.dl.x, y = g.ol.y + t * g.dl.y;
@@ -328,7 +328,7 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                     for (int k = 0; k < sc.n_stages; ++k) {
                         so[k] = oc; sd[k] = dc; sv[k] = val;
                         int mi; float t;
-                        if (!stage_select(sc.stages[k].n, rec, sc.stages[k].verts, oc, dc, mi, t) ||
+                        if (!stage_select(sc.stages[k].n, rec, sc.stages[k].verts, !cull, oc, dc, mi, t) ||
                             occluded(ob, oc, dc, nullptr, 0, 0)) { alive = false; break; }
                         smi[k] = mi; st_t[k] = t;
                         const StageGeom g = stage_geometry(rec + (size_t)mi * STAGE_REC, oc, dc, t);

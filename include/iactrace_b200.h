@@ -109,7 +109,7 @@ typedef struct IactScene {
     int32_t n_stages;                                           /* stages >= 1      */
     IactMirrorStage stages[IACT_MAX_STAGES];
     IactSensor sensor;
-    int32_t cull;          /* 1 = conservative beam/obstruction culling (default), 0 = brute force */
+    int32_t cull;          /* 1 = conservative beam/obstruction culling + early Newton exit (default; results identical), 0 = the reference's literal brute force */
 } IactScene;
 
 /* Stage-0 facet parameters in the LOCAL frame: the differentiable inputs. */

@@ -116,3 +116,45 @@ def test_sensor_accumulate_entry_point():
         if idx == 0:
             torch.testing.assert_close(img, ref, rtol=1e-5, atol=1e-8)
         assert img.shape == ref.shape
+
+
+def test_stage_leg_culling_and_newton_exit_are_exact():
+    """The leg towards the secondary is culled per 32-ray run (occluded_leg_culled) on a spatially binned
+    sample table, and the Newton scan leaves early once t repeats: both must reproduce the brute-force,
+    unbinned run bit for bit, per ray, with obstruction clouds of every type around the light path."""
+    from iactrace_b200 import config as Rm
+    rng = np.random.default_rng(7)
+    base = build_telescope(cassegrain_config(True), I.MCIntegrator(320), I.random.key(3))
+    src, val = _star_field(9, seed=1)
+    obs = list(cassegrain_config(True)["obstructions"])
+    prims = [Cylinder(o["p1"], o["p2"], o["r"]) if o["type"] == "cylinder" else
+             Box(o["p1"], o["p2"]) if o["type"] == "box" else Sphere(o["center"], o["r"]) for o in obs]
+    for _ in range(30):                                   # clutter between the primary and the secondary
+        a = rng.uniform([-3, -3, 0.5], [3, 3, 6.5])
+        prims.append(Cylinder(a, a + rng.normal(size=3) * rng.uniform(0.1, 1.5), float(rng.uniform(0.005, 0.05))))
+    for _ in range(5):
+        prims.append(Sphere(rng.uniform([-3, -3, 0.5], [3, 3, 6.5]), float(rng.uniform(0.02, 0.15))))
+        a = rng.uniform([-3, -3, 0.5], [3, 3, 6.5])
+        prims.append(Box(a, a + rng.uniform(0.02, 0.3, 3)))
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        prims.append(OrientedBox(rng.uniform([-3, -3, 0.5], [3, 3, 6.5]), rng.uniform(0.02, 0.2, 3), q.astype(np.float32)))
+        v0 = rng.uniform([-3, -3, 0.5], [3, 3, 6.5])
+        prims.append(Triangle(v0, v0 + rng.normal(size=3) * 0.3, v0 + rng.normal(size=3) * 0.3))
+    for plist in (prims[:6], prims):
+        tel = I.Telescope(base.mirror_groups, group_obstructions(plist), base.sensors)
+        out = []
+        for cull, bin_min in ((True, 256), (False, 0)):
+            Rm.cull_obstructions, old_bin = cull, Rm.bin_samples_min
+            Rm.bin_samples_min = bin_min
+            try:
+                tel._cache.pop("world", None)
+                xy, v = render_debug(tel, src, val, "parallel", 0)
+                img = render(tel, src, val, "parallel", 0)
+                out.append((xy.cpu().numpy(), v.cpu().numpy(), img.cpu().numpy()))
+            finally:
+                Rm.cull_obstructions, Rm.bin_samples_min = True, old_bin
+        assert np.array_equal(out[0][1], out[1][1])
+        assert np.array_equal(out[0][0], out[1][0])
+        np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-4, atol=1e-6 * out[1][2].max())
+        lit = (out[0][1] != 0).mean()
+        assert 0.05 < lit < 0.95, lit
