@@ -58,14 +58,8 @@ __device__ __forceinline__ bool beam_keeps_capsule(const Beam& b, V3 p1, V3 p2, 
 }
 
 __device__ __forceinline__ bool keep_primitive(const ObsSmem& ob, const Beam& b, int id) {
-    if (id < ob.n_cyl) {
-        const float* c = ob.ccyl; const int n = ob.n_cyl;
-        return beam_keeps_capsule(b, v3(c[id], c[n + id], c[2 * n + id]), v3(c[3 * n + id], c[4 * n + id], c[5 * n + id]), c[6 * n + id]);
-    }
-    id -= ob.n_cyl;
-    const float* c = ob.cball; const int n = ob.n_rest;
-    const V3 m = v3(c[id], c[n + id], c[2 * n + id]);
-    return beam_keeps_capsule(b, m, m, c[3 * n + id]);
+    const float* c = ob.cprox; const int n = ob.n_cyl + ob.n_rest;
+    return beam_keeps_capsule(b, v3(c[id], c[n + id], c[2 * n + id]), v3(c[3 * n + id], c[4 * n + id], c[5 * n + id]), c[6 * n + id]);
 }
 
 // Warp-cooperative compaction of the primitives a beam can reach.  `cand` (may be null = all

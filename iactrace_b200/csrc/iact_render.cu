@@ -233,7 +233,7 @@ struct PixCache {
 #define IACT_MIN_BLOCKS 4
 #endif
 #ifndef IACT_MIN_BLOCKS_STAGES
-#define IACT_MIN_BLOCKS_STAGES 2
+#define IACT_MIN_BLOCKS_STAGES 3
 #endif
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
 __global__ void __launch_bounds__(256, STAGES ? IACT_MIN_BLOCKS_STAGES : IACT_MIN_BLOCKS)

@@ -122,7 +122,7 @@ __device__ __forceinline__ bool stage_select(int n_mirrors, const float* rec, co
         SurfRef s;
         s.c = r[8]; s.k = r[9]; s.kc2 = r[33]; s.n_asph = (int)r[10]; s.asph = r + 11; s.full_scan = full_scan;
         V3 pl, nl;
-        float t = surface_intersect(s, r[6], r[7], mulT(R, o - pos), mulT(R, d), pl, nl);
+        float t = surface_intersect(s, r[6], r[7], r[34], mulT(R, o - pos), mulT(R, d), pl, nl);
         bool inside;
         if (r[19] == 0.f) {
             inside = pl.x * pl.x + pl.y * pl.y <= r[20] * r[20];
