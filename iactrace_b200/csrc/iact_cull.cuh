@@ -350,5 +350,4 @@ LaunchPlan make_plan(const SceneDev& d, int S, int mode) {
     return p;
 }
 
-
 }  // namespace

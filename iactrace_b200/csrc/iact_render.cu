@@ -197,8 +197,10 @@ struct SoftHexCache {
 
 // Per-warp-item pixel cache: the rays of one (facet, source) pair land in 1-3 hex pixels, so the warp
 // keeps up to three (pixel, per-lane partial sum) slots in registers across all its iterations and
-// touches the shared histogram once per slot at the end of the item; rays outside the three cached
-// pixels fall back to a direct shared atomic.  Slot pixels are warp-uniform.
+// touches the shared histogram only when a slot is given up.  The cache outlives the warp items (the next
+// facet of the same source feeds the same pixels); when a fourth pixel shows up the three slots are flushed
+// and reused, and only an iteration that itself holds more than three distinct pixels falls back to direct
+// shared atomics.  Slot pixels are warp-uniform.
 struct PixCache {
     int p0, p1, p2;
     float a0, a1, a2;
@@ -207,7 +209,15 @@ struct PixCache {
     __device__ __forceinline__ void add(float* hist, int pix, float val) {
         bool matched = (pix < 0) | (pix == p0) | (pix == p1) | (pix == p2);
         unsigned un = __ballot_sync(0xffffffffu, !matched);
-        while (un != 0u && p2 < 0) {                        // a free slot and an unmatched pixel
+        bool flushed = false;
+        while (un != 0u) {
+            if (p2 >= 0) {                                  // no free slot
+                if (flushed) break;
+                flush(hist); reset(); flushed = true;
+                matched = pix < 0;
+                un = __ballot_sync(0xffffffffu, !matched);
+                continue;
+            }
             const int lp = __shfl_sync(0xffffffffu, pix, __ffs(un) - 1);
             if (p0 < 0) p0 = lp; else if (p1 < 0) p1 = lp; else p2 = lp;
             matched = matched | (pix == lp);
@@ -235,36 +245,125 @@ struct PixCache {
 #ifndef IACT_MIN_BLOCKS_STAGES
 #define IACT_MIN_BLOCKS_STAGES 3
 #endif
+// Everything a warp needs to trace its rays, fixed for the lifetime of the block.
+struct TraceCtx {
+    ObsSmem ob;
+    const float* stage_rec;
+    float* hist;
+    const short* lut;
+    unsigned short* list;
+    bool cull, soft;
+};
+
+// Per-block set-up shared by the trace kernels: obstruction tables, stage records, histogram, lookup table
+// and the per-warp candidate lists in shared memory.  Ends with a block barrier.
+template <int SENS, int MODE, bool STAGES>
+__device__ __forceinline__ void trace_setup(const SceneDev& sc, float* smem, TraceCtx& cx) {
+    cx.cull = sc.cull != 0;
+    stage_obstructions(sc, smem, cx.ob, cx.cull);
+    const int n_obs = cx.ob.n_cyl + cx.ob.n_rest;
+    float* p = smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri, cx.cull);
+    cx.stage_rec = p;
+    if (STAGES) { stage_mirrors(sc, p); p += stage_floats(sc); }
+    cx.hist = nullptr;
+    cx.lut = nullptr;
+    if (SENS != SENS_SQUARE) {
+        if (MODE != MODE_DEBUG) { cx.hist = p; p += sc.sens.npix; }
+        short* l = reinterpret_cast<short*>(p);
+        for (int i = threadIdx.x; i < sc.sens.tq * sc.sens.tr; i += blockDim.x) l[i] = (short)sc.sens.lookup[i];
+        cx.lut = l;
+        p += (sc.sens.tq * sc.sens.tr + 1) / 2;
+        if (cx.hist) for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) cx.hist[i] = 0.f;
+    }
+    const int warp = threadIdx.x >> 5;
+    cx.list = cx.cull ? reinterpret_cast<unsigned short*>(p) + (size_t)warp * ((n_obs + 1) & ~1) : nullptr;
+    cx.soft = SENS == SENS_SQUARE ? sc.sens.kind == IACT_SENSOR_SOFT_SQUARE : SENS == SENS_SOFT_HEX;
+    __syncthreads();
+}
+
+// One ray from table row (a, b) of a facet towards source `src`: shadow of the incoming leg, reflection,
+// optical stages >= 1, sensor plane, binning (or the per-ray debug record at index ri).  Called by all 32
+// lanes; `live` = this lane holds a real ray.
+template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
+__device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx, float4 a, float4 b, V3 src, float sval, bool live,
+                                          int n_list_cyl, int n_list, unsigned sub_mask, size_t ri, bool soft7,
+                                          PixCache& cache, SoftHexCache& scache, float* __restrict__ gout,
+                                          float* __restrict__ out_val, int* __restrict__ out_pix) {
+    const ObsSmem& ob = cx.ob;
+    V3 o = v3(a.x, a.y, a.z);
+    const V3 n = v3(b.x, b.y, b.z);
+    // render.py:129-133
+    V3 d;
+    if (SRC == IACT_SOURCE_POINT) {
+        d = o - src;
+        d = frsqrt_nr(dot(d, d)) * d;
+    } else {
+        d = src;
+    }
+    // render.py:138 shadow of the incoming leg (infinite ray back towards the source)
+    const bool blocked = occluded<SUB>(ob, o, -d, cx.list, n_list_cyl, n_list, sub_mask);
+    // render.py:140-141, reflection.py:17-19
+    const float c = dot(d, n);
+    d = d - (2.0f * c) * n;
+    float val = blocked ? 0.f : (sval * (-c)) * a.w;         // a.w = 1/weight (transform_kernel)
+    if (STAGES) {
+        const float* rec = cx.stage_rec;
+        for (int st = 0; st < sc.n_stages; ++st) {
+            const bool leg_blocked = cx.cull ? occluded_leg_culled(ob, o, d, val != 0.f)
+                                             : occluded(ob, o, d, nullptr, 0, 0);
+            reflect_at_stage(sc.stages[st].n, rec, sc.stages[st].verts, leg_blocked, !cx.cull, o, d, val);
+            rec += (size_t)sc.stages[st].n * STAGE_REC;
+        }
+    }
+    // render.py:152-155
+    float x, y;
+    plane_hit(sc.sens, o, d, x, y);
+    if (MODE == MODE_DEBUG) {
+        if (live) {
+            gout[2 * ri] = x; gout[2 * ri + 1] = y; out_val[ri] = val;
+            if (out_pix) {
+                int pix = -1;
+                if (!cx.soft) pix = SENS != SENS_SQUARE ? hex_pixel(sc.sens, cx.lut, x, y) : square_pixel(sc.sens, x, y);
+                out_pix[ri] = pix;
+            }
+        }
+    } else {
+        const bool add = live && val != 0.f;
+        if (SENS == SENS_SOFT_HEX) {
+            if (soft7) scache.add(sc.sens, cx.lut, add, x, y, val, cx.hist);
+            else splat_soft_hex_warp(sc.sens, cx.lut, add, x, y, val, cx.hist);
+        } else if (SENS == SENS_HEX) {
+            cache.add(cx.hist, add ? hex_pixel(sc.sens, cx.lut, x, y) : -1, val);
+        } else if (add) {
+            if (cx.soft) splat_soft_square(sc.sens, x, y, val, gout);
+            else { const int pix = square_pixel(sc.sens, x, y); if (pix >= 0) atomicAdd(gout + pix, val); }
+        }
+    }
+}
+
+// Level-2 candidate list of one beam into the warp's shared-memory list.
+__device__ __forceinline__ int item_list(const TraceCtx& cx, const FacetLists& fl, const Beam& beam, int f, int& n_list_cyl) {
+    const int n_obs = cx.ob.n_cyl + cx.ob.n_rest;
+    const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
+    if (cnt.x >= 0) return build_list(cx.ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, cx.list, n_list_cyl);
+    return build_list(cx.ob, beam, (const unsigned short*)nullptr, cx.ob.n_cyl, n_obs, cx.list, n_list_cyl);
+}
+
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
 __global__ void __launch_bounds__(256, STAGES ? IACT_MIN_BLOCKS_STAGES : IACT_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
              const LaunchPlan plan, const FacetLists fl, float* __restrict__ out, float* __restrict__ out_val,
              int* __restrict__ out_pix) {
     extern __shared__ __align__(16) float smem[];
-    ObsSmem ob;
-    const bool cull = sc.cull != 0;
-    stage_obstructions(sc, smem, ob, cull);
-    const int n_obs = ob.n_cyl + ob.n_rest;
-    float* p = smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri, cull);
-    const float* stage_rec = p;
-    if (STAGES) { stage_mirrors(sc, p); p += stage_floats(sc); }
-    float* hist = nullptr;
-    const short* lut = nullptr;
-    if (SENS != SENS_SQUARE) {
-        if (MODE != MODE_DEBUG) { hist = p; p += sc.sens.npix; }
-        short* l = reinterpret_cast<short*>(p);
-        for (int i = threadIdx.x; i < sc.sens.tq * sc.sens.tr; i += blockDim.x) l[i] = (short)sc.sens.lookup[i];
-        lut = l;
-        p += (sc.sens.tq * sc.sens.tr + 1) / 2;
-        if (hist) for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) hist[i] = 0.f;
-    }
+    TraceCtx cx;
+    trace_setup<SENS, MODE, STAGES>(sc, smem, cx);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    unsigned short* list = cull ? reinterpret_cast<unsigned short*>(p) + (size_t)warp * ((n_obs + 1) & ~1) : nullptr;
-    __syncthreads();
-
     const int M = sc.M;
-    const bool soft = SENS == SENS_SQUARE ? sc.sens.kind == IACT_SENSOR_SOFT_SQUARE : SENS == SENS_SOFT_HEX;
     const size_t npix = SENS != SENS_SQUARE ? (size_t)sc.sens.npix : (size_t)sc.sens.W * sc.sens.H;
+    // the pixel cache outlives the warp items: the next facet of the same source feeds the same few pixels,
+    // and a new pixel evicts by flushing (PixCache::add); it is emptied before the histogram is read
+    PixCache cache;
+    cache.reset();
 
     for (long long item = blockIdx.x; item < plan.n_items; item += gridDim.x) {
         const int s = (int)(item / plan.n_chunks), ch = (int)(item - (long long)s * plan.n_chunks);
@@ -280,20 +379,13 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             const int f = f0 + fi;
             const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
             int n_list = 0, n_list_cyl = 0;
-            if (cull) {
-                const Beam beam = make_beam<SRC>(__ldg(sc.bounds + f), src);
-                const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
-                if (cnt.x >= 0) n_list = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, n_list_cyl);
-                else            n_list = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, n_list_cyl);
-            }
+            if (cx.cull) n_list = item_list(cx, fl, make_beam<SRC>(__ldg(sc.bounds + f), src), f, n_list_cyl);
             const float4* tab = sc.world + ((size_t)f * M) * 2;
-            PixCache cache;
-            cache.reset();
             SoftHexCache scache;
             const bool soft7 = SENS == SENS_SOFT_HEX && MODE != MODE_DEBUG && sc.sens.ksize == 1;
             if (soft7) scache.reset();
             // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
-            const bool sub_beams = SUB && cull && n_list >= 2 && n_list <= 32;   // one candidate: the test costs what it saves
+            const bool sub_beams = SUB && cx.cull && n_list >= 2 && n_list <= 32;   // one candidate: the test costs what it saves
             const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
             for (int mb = m0; mb < m1; mb += 32) {
                 const int m = mb + lane;
@@ -303,80 +395,34 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 unsigned sub_mask = 0xffffffffu;
                 if (SUB && sub_beams) {
                     const Beam cb = make_beam<SRC>(__ldg(cbs + (mb >> 5)), src);
-                    sub_mask = __ballot_sync(0xffffffffu, lane < n_list && (!cb.ok || keep_primitive(ob, cb, list[lane])));
+                    sub_mask = __ballot_sync(0xffffffffu, lane < n_list && (!cb.ok || keep_primitive(cx.ob, cb, cx.list[lane])));
                 }
-                V3 o = v3(a.x, a.y, a.z);
-                const V3 n = v3(b.x, b.y, b.z);
-                // render.py:129-133
-                V3 d;
-                if (SRC == IACT_SOURCE_POINT) {
-                    d = o - src;
-                    d = frsqrt_nr(dot(d, d)) * d;
-                } else {
-                    d = src;
-                }
-                // render.py:138 shadow of the incoming leg (infinite ray back towards the source)
-                const bool blocked = occluded<SUB>(ob, o, -d, list, n_list_cyl, n_list, sub_mask);
-                // render.py:140-141, reflection.py:17-19
-                const float c = dot(d, n);
-                d = d - (2.0f * c) * n;
-                float val = blocked ? 0.f : (sval * (-c)) * a.w;         // a.w = 1/weight (transform_kernel)
-                if (STAGES) {
-                    const float* rec = stage_rec;
-                    for (int st = 0; st < sc.n_stages; ++st) {
-                        const bool leg_blocked = cull ? occluded_leg_culled(ob, o, d, val != 0.f)
-                                                      : occluded(ob, o, d, nullptr, 0, 0);
-                        reflect_at_stage(sc.stages[st].n, rec, sc.stages[st].verts, leg_blocked, !cull, o, d, val);
-                        rec += (size_t)sc.stages[st].n * STAGE_REC;
-                    }
-                }
-                // render.py:152-155
-                float x, y;
-                plane_hit(sc.sens, o, d, x, y);
-                if (MODE == MODE_DEBUG) {
-                    if (live) {
-                        const size_t ri = ((size_t)f * plan.S + s) * M + __float_as_int(b.w);   // original sample index
-                        out[2 * ri] = x; out[2 * ri + 1] = y; out_val[ri] = val;
-                        if (out_pix) {
-                            int pix = -1;
-                            if (!soft) pix = SENS != SENS_SQUARE ? hex_pixel(sc.sens, lut, x, y) : square_pixel(sc.sens, x, y);
-                            out_pix[ri] = pix;
-                        }
-                    }
-                } else {
-                    const bool add = live && val != 0.f;
-                    if (SENS == SENS_SOFT_HEX) {
-                        if (soft7) scache.add(sc.sens, lut, add, x, y, val, hist);
-                        else splat_soft_hex_warp(sc.sens, lut, add, x, y, val, hist);
-                    } else if (SENS == SENS_HEX) {
-                        cache.add(hist, add ? hex_pixel(sc.sens, lut, x, y) : -1, val);
-                    } else if (add) {
-                        if (soft) splat_soft_square(sc.sens, x, y, val, gout);
-                        else { const int pix = square_pixel(sc.sens, x, y); if (pix >= 0) atomicAdd(gout + pix, val); }
-                    }
-                }
+                const size_t ri = ((size_t)f * plan.S + s) * M + __float_as_int(b.w);   // debug: original sample index
+                trace_ray<SRC, SENS, MODE, STAGES, SUB>(sc, cx, a, b, src, sval, live, n_list_cyl, n_list, sub_mask, ri, soft7,
+                                                        cache, scache, gout, out_val, out_pix);
             }
-            if (SENS == SENS_HEX && MODE != MODE_DEBUG) cache.flush(hist);
-            if (SENS == SENS_SOFT_HEX && soft7) scache.flush(sc.sens, lut, hist);
+            if (SENS == SENS_SOFT_HEX && soft7) scache.flush(sc.sens, cx.lut, cx.hist);
             __syncwarp();
         }
         if (MODE == MODE_MATRIX && SENS != SENS_SQUARE) {
+            if (SENS == SENS_HEX) { cache.flush(cx.hist); cache.reset(); }
             __syncthreads();
             if (plan.n_chunks == 1) {
-                for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) { gout[i] = hist[i]; hist[i] = 0.f; }
+                for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) { gout[i] = cx.hist[i]; cx.hist[i] = 0.f; }
             } else {
                 for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) {
-                    const float v = hist[i];
-                    if (v != 0.f) { atomicAdd(gout + i, v); hist[i] = 0.f; }
+                    const float v = cx.hist[i];
+                    if (v != 0.f) { atomicAdd(gout + i, v); cx.hist[i] = 0.f; }
                 }
             }
             __syncthreads();
         }
     }
     if (MODE == MODE_RENDER && SENS != SENS_SQUARE) {
+        if (SENS == SENS_HEX) cache.flush(cx.hist);
         __syncthreads();
         for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) {
-            const float v = hist[i];
+            const float v = cx.hist[i];
             if (v != 0.f) atomicAdd(out + i, v);
         }
     }

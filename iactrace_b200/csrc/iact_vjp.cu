@@ -237,8 +237,14 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+#ifndef IACT_VJP_MIN_BLOCKS
+#define IACT_VJP_MIN_BLOCKS 2
+#endif
+#ifndef IACT_VJP_MIN_BLOCKS_STAGES
+#define IACT_VJP_MIN_BLOCKS_STAGES 2
+#endif
 template <int SRC, int SENS, bool STAGES>
-__global__ void __launch_bounds__(256, STAGES ? 1 : 2)
+__global__ void __launch_bounds__(256, STAGES ? IACT_VJP_MIN_BLOCKS_STAGES : IACT_VJP_MIN_BLOCKS)
 vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float* __restrict__ sources,
            const float* __restrict__ values, const LaunchPlan plan, const FacetLists fl,
            const float* __restrict__ G, const GradsDev gr) {
