@@ -57,7 +57,7 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
                 const float g = (xi >= 0 && xi < se.W && yi >= 0 && yi < se.H) ? __ldg(G + (size_t)yi * se.W + xi) : 0.f;
                 D += w; Nn += g * w; gx += g * dwx; gy += g * dwy; wx += dwx; wy += dwy;
             }
-        const float invD = 1.0f / D;
+        const float invD = frcp_nr(D);
         dval = Nn * invD;
         dx = (gx - dval * wx) * invD * se.inv_dx;
         dy = (gy - dval * wy) * invD * se.inv_dy;
@@ -97,7 +97,7 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
             for (int orr = -K; orr <= K; ++orr)
                 if (max(max(abs(oq), abs(orr)), abs(oq + orr)) <= K) tap(oq, orr);
     }
-    const float invD = 1.0f / D;
+    const float invD = frcp_nr(D);
     dval = Nn * invD;
     const float dxg = (gx - dval * wx) * invD, dyg = (gy - dval * wy) * invD;
     // (xg, yg) = Rot(-grid_rotation) (x - off):  xg = cr tx - sr ty, yg = sr tx + cr ty
@@ -313,15 +313,16 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 const V3 o = mul(R, pl) + pos;
                 const V3 nq = nl + scale * dl;                      // local perturbed normal
                 const V3 nw = mul(R, nq);
-                const float inv_nw = 1.0f / sqrtf(dot(nw, nw));
+                const float inv_nw = frsqrt_nr(dot(nw, nw));          // <= 1 ulp, no IEEE slow path (as the forward)
                 const V3 n = inv_nw * nw;
                 V3 d; float inv_a = 0.f;
-                if (SRC == IACT_SOURCE_POINT) { d = o - src; inv_a = 1.0f / sqrtf(dot(d, d)); d = inv_a * d; }
+                if (SRC == IACT_SOURCE_POINT) { d = o - src; inv_a = frsqrt_nr(dot(d, d)); d = inv_a * d; }
                 else d = src;
                 if (occluded(ob, o, -d, list, n_list_cyl, n_list)) continue;
                 const float c = dot(d, n);
                 const V3 r = d - (2.0f * c) * n;
-                const float val0 = (sval * (-c)) / w;
+                const float inv_w = frcp_nr(w);
+                const float val0 = (sval * (-c)) * inv_w;
                 // optical stages >= 1: forward with the state the reverse pass needs
                 V3 so[IACT_MAX_STAGES], sd[IACT_MAX_STAGES];
                 float st_t[IACT_MAX_STAGES], sv[IACT_MAX_STAGES];
@@ -349,7 +350,8 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 if (!alive) continue;
                 const float B = dot(dc, ns), ndoto = dot(oc, ns);
                 if (fabsf(B) < 1e-10f) continue;
-                const float t = (se.ndotp - ndoto) / B;
+                const float inv_B = frcp_nr(B);
+                const float t = (se.ndotp - ndoto) * inv_B;
                 if (t <= 0.f) continue;
                 const V3 h = oc + t * dc - ps;
                 const float x = dot(h, u1), y = dot(h, u2);
@@ -365,7 +367,7 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                     g_o = g_h;
                     const float g_t = dot(g_h, dc);
                     g_r = t * g_h;
-                    const float gA = g_t / B, gB = -g_t * t / B;
+                    const float gA = g_t * inv_B, gB = -g_t * t * inv_B;
                     g_ns = g_ns + gA * (ps - oc) + gB * dc;
                     g_ps = g_ps + gA * ns;
                     g_o = g_o - gA * ns;
@@ -397,9 +399,9 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                     }
                 }
                 // val = v (-c)/w
-                float g_c = -dval * sval / w;
-                g_val += dval * (-c) / w;
-                if (gr.weights) atomicAdd(gr.weights + (size_t)f * M + m, -dval * val0 / w);
+                float g_c = -dval * sval * inv_w;
+                g_val += dval * (-c) * inv_w;
+                if (gr.weights) atomicAdd(gr.weights + (size_t)f * M + m, -dval * val0 * inv_w);
                 // r = d - 2 c n ; c = d.n
                 g_c += -2.0f * dot(g_r, n);
                 V3 g_d = g_r + g_c * n;
