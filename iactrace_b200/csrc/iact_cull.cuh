@@ -15,6 +15,11 @@ struct LaunchPlan {
     long long n_items;
 };
 
+// Work queue of the forward kernels: a global counter hands out units.  Render / debug: a unit is
+// (source, run of `facets_per_unit` facets, sample part) and is pulled by one warp; response matrix: a unit
+// is a block item of the LaunchPlan.  counter == nullptr = static grid-stride split.
+struct QueuePlan { int facets_per_unit, runs, msplit, msize; long long n_units; unsigned long long* counter; };
+
 // Level-1 culling output: per facet a list of primitive ids (cylinders first) and its two counts;
 // count.x < 0 means "no facet-level culling for this facet" (degenerate beam): use every primitive.
 struct FacetLists { const unsigned short* ids; const int2* count; int stride; };
@@ -348,6 +353,24 @@ LaunchPlan make_plan(const SceneDev& d, int S, int mode) {
     p.msplit = (d.M + p.msize - 1) / std::max(p.msize, 1);
     p.n_items = (long long)S * p.n_chunks;
     return p;
+}
+
+// Units of the render / debug work queue: about 64 per resident warp when the job is large (short tail, one
+// atomic per ~1e4 warp instructions); small jobs are split along the samples so that every warp gets work.
+QueuePlan make_queue_plan(const SceneDev& d, int S, long long resident_warps) {
+    QueuePlan q;
+    const long long pairs = (long long)S * d.F;
+    q.facets_per_unit = (int)std::max(1LL, std::min(8LL, pairs / (resident_warps * 64)));
+    q.runs = (d.F + q.facets_per_unit - 1) / q.facets_per_unit;
+    const long long base = (long long)S * q.runs;
+    long long ms = 1;
+    if (base < resident_warps * 4) ms = std::min<long long>((d.M + 31) / 32, (resident_warps * 4 + base - 1) / std::max(base, 1LL));
+    ms = std::max(ms, 1LL);
+    q.msize = (int)(((d.M + ms - 1) / ms + 31) / 32 * 32);
+    q.msplit = (d.M + q.msize - 1) / std::max(q.msize, 1);
+    q.n_units = base * q.msplit;
+    q.counter = nullptr;
+    return q;
 }
 
 }  // namespace

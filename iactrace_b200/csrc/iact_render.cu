@@ -204,9 +204,10 @@ struct SoftHexCache {
 struct PixCache {
     int p0, p1, p2;
     float a0, a1, a2;
-    __device__ __forceinline__ void reset() { p0 = p1 = p2 = -1; a0 = a1 = a2 = 0.f; }
-    // must be called by all 32 lanes; pix < 0 = nothing to add
-    __device__ __forceinline__ void add(float* hist, int pix, float val) {
+    float cx, cy;            // centre of slot 0's hexagon in grid coordinates (1e30 = slot 0 empty): the fast path of trace_ray
+    __device__ __forceinline__ void reset() { p0 = p1 = p2 = -1; a0 = a1 = a2 = 0.f; cx = cy = 1e30f; }
+    // must be called by all 32 lanes; pix < 0 = nothing to add; (pcx, pcy) = centre of the lane's hexagon
+    __device__ __forceinline__ void add(float* hist, int pix, float val, float pcx, float pcy) {
         bool matched = (pix < 0) | (pix == p0) | (pix == p1) | (pix == p2);
         unsigned un = __ballot_sync(0xffffffffu, !matched);
         bool flushed = false;
@@ -218,8 +219,12 @@ struct PixCache {
                 un = __ballot_sync(0xffffffffu, !matched);
                 continue;
             }
-            const int lp = __shfl_sync(0xffffffffu, pix, __ffs(un) - 1);
-            if (p0 < 0) p0 = lp; else if (p1 < 0) p1 = lp; else p2 = lp;
+            const int leader = __ffs(un) - 1;
+            const int lp = __shfl_sync(0xffffffffu, pix, leader);
+            if (p0 < 0) {
+                p0 = lp;
+                cx = __shfl_sync(0xffffffffu, pcx, leader); cy = __shfl_sync(0xffffffffu, pcy, leader);
+            } else if (p1 < 0) p1 = lp; else p2 = lp;
             matched = matched | (pix == lp);
             un = __ballot_sync(0xffffffffu, !matched);
         }
@@ -228,6 +233,18 @@ struct PixCache {
             else if (pix == p1) a1 += val;
             else if (pix == p2) a2 += val;
             else atomicAdd(hist + pix, val);
+        }
+        // the pixel of the first adding lane moves to slot 0, the one the next iteration's fast path tests
+        const unsigned am = __ballot_sync(0xffffffffu, pix >= 0);
+        if (am != 0u) {
+            const int leader = __ffs(am) - 1;
+            const int lp = __shfl_sync(0xffffffffu, pix, leader);
+            if (lp != p0 && (lp == p1 || lp == p2)) {
+                cx = __shfl_sync(0xffffffffu, pcx, leader); cy = __shfl_sync(0xffffffffu, pcy, leader);
+                if (lp == p1) { p1 = p0; const float t = a1; a1 = a0; a0 = t; }
+                else          { p2 = p0; const float t = a2; a2 = a0; a0 = t; }
+                p0 = lp;
+            }
         }
     }
     __device__ __forceinline__ void flush(float* hist) {
@@ -239,6 +256,9 @@ struct PixCache {
 };
 
 // ---------------------------------------------------------------- the kernel
+#ifndef IACT_HEX_FAST
+#define IACT_HEX_FAST 1
+#endif
 #ifndef IACT_MIN_BLOCKS
 #define IACT_MIN_BLOCKS 4
 #endif
@@ -333,7 +353,20 @@ __device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx
             if (soft7) scache.add(sc.sens, cx.lut, add, x, y, val, cx.hist);
             else splat_soft_hex_warp(sc.sens, cx.lut, add, x, y, val, cx.hist);
         } else if (SENS == SENS_HEX) {
-            cache.add(cx.hist, add ? hex_pixel(sc.sens, cx.lut, x, y) : -1, val);
+            // Fast path: the rays of one (facet, source) pair mostly share their hexagon with the previous iteration.
+            // A hit whose hex norm about the cached centre is < 0.9999 lies strictly inside that cell, so the cube
+            // rounding (hexagonal.py:32-39) would return it, and the edge rejection (:184-190) sees the identical
+            // norm; when that holds for every adding lane the rounding, the table lookup and the slot search are skipped.
+            float xg, yg; hex_grid_coords(sc.sens, x, y, xg, yg);
+            const float fdx = fabsf(xg - cache.cx), fdy = fabsf(yg - cache.cy);
+            const float fhn = fmaxf(fdx, 0.5f * fdx + 0.8660254037844386f * fdy) * sc.sens.inv_inradius;
+            if (IACT_HEX_FAST && __all_sync(0xffffffffu, !add || fhn < 0.9999f)) {
+                if (add && !(fhn > sc.sens.edge_thr)) cache.a0 += val;
+            } else {
+                float pcx, pcy;
+                const int pix = hex_pixel_grid(sc.sens, cx.lut, xg, yg, pcx, pcy);
+                cache.add(cx.hist, add ? pix : -1, val, pcx, pcy);
+            }
         } else if (add) {
             if (cx.soft) splat_soft_square(sc.sens, x, y, val, gout);
             else { const int pix = square_pixel(sc.sens, x, y); if (pix >= 0) atomicAdd(gout + pix, val); }
@@ -349,12 +382,52 @@ __device__ __forceinline__ int item_list(const TraceCtx& cx, const FacetLists& f
     return build_list(cx.ob, beam, (const unsigned short*)nullptr, cx.ob.n_cyl, n_obs, cx.list, n_list_cyl);
 }
 
+// One warp item: rays m0..m1 of facet f seen from source s (level-2 list, optional level-3 masks, per-ray trace).
+template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
+__device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& cx, const FacetLists& fl, int S, int s, V3 src, float sval,
+                                           int f, int m0, int m1, PixCache& cache, float* __restrict__ gout,
+                                           float* __restrict__ out_val, int* __restrict__ out_pix) {
+    const int lane = threadIdx.x & 31;
+    const int M = sc.M;
+    int n_list = 0, n_list_cyl = 0;
+    if (cx.cull) n_list = item_list(cx, fl, make_beam<SRC>(__ldg(sc.bounds + f), src), f, n_list_cyl);
+    const float4* tab = sc.world + ((size_t)f * M) * 2;
+    SoftHexCache scache;
+    const bool soft7 = SENS == SENS_SOFT_HEX && MODE != MODE_DEBUG && sc.sens.ksize == 1;
+    if (soft7) scache.reset();
+    // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
+    const bool sub_beams = SUB && cx.cull && n_list >= 2 && n_list <= 32;   // one candidate: the test costs what it saves
+    const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
+    for (int mb = m0; mb < m1; mb += 32) {
+        const int m = mb + lane;
+        const bool live = m < m1;
+        const int mm = live ? m : m1 - 1;
+        const float4 a = __ldg(tab + 2 * mm), b = __ldg(tab + 2 * mm + 1);
+        unsigned sub_mask = 0xffffffffu;
+        if (SUB && sub_beams) {
+            const Beam cb = make_beam<SRC>(__ldg(cbs + (mb >> 5)), src);
+            sub_mask = __ballot_sync(0xffffffffu, lane < n_list && (!cb.ok || keep_primitive(cx.ob, cb, cx.list[lane])));
+        }
+        const size_t ri = ((size_t)f * S + s) * M + __float_as_int(b.w);   // debug: original sample index
+        trace_ray<SRC, SENS, MODE, STAGES, SUB>(sc, cx, a, b, src, sval, live, n_list_cyl, n_list, sub_mask, ri, soft7,
+                                                cache, scache, gout, out_val, out_pix);
+    }
+    if (SENS == SENS_SOFT_HEX && soft7) scache.flush(sc.sens, cx.lut, cx.hist);
+    __syncwarp();
+}
+
+// Work distribution.  Render / debug: every warp pulls units (source, run of facets, sample part) from a
+// global counter (QueuePlan), so no warp idles while another still has a backlog -- with the static
+// grid-stride split 18 % of the resident warp slots were empty (blocks and warps of unequal cost finishing
+// early).  Response matrix: one block owns a source row (its histogram is the row), so whole block items are
+// pulled from the same counter.  queue.counter == nullptr selects the static split.
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
 __global__ void __launch_bounds__(256, STAGES ? IACT_MIN_BLOCKS_STAGES : IACT_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
-             const LaunchPlan plan, const FacetLists fl, float* __restrict__ out, float* __restrict__ out_val,
-             int* __restrict__ out_pix) {
+             const LaunchPlan plan, const QueuePlan queue, const FacetLists fl, float* __restrict__ out,
+             float* __restrict__ out_val, int* __restrict__ out_pix) {
     extern __shared__ __align__(16) float smem[];
+    __shared__ long long s_item[2];
     TraceCtx cx;
     trace_setup<SENS, MODE, STAGES>(sc, smem, cx);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -365,57 +438,67 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     PixCache cache;
     cache.reset();
 
-    for (long long item = blockIdx.x; item < plan.n_items; item += gridDim.x) {
-        const int s = (int)(item / plan.n_chunks), ch = (int)(item - (long long)s * plan.n_chunks);
-        const int f0 = ch * plan.chunk_facets, f1 = min(sc.F, f0 + plan.chunk_facets);
-        const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
-        const float sval = __ldg(values + s);
-        float* gout = MODE == MODE_MATRIX ? out + (size_t)s * npix : out;
-
-        const int n_w = (f1 - f0) * plan.msplit;
-        for (int wi = warp; wi < n_w; wi += nwarps) {
-            int fi = wi, part = 0;
-            if (plan.msplit > 1) { fi = wi / plan.msplit; part = wi - fi * plan.msplit; }
-            const int f = f0 + fi;
-            const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
-            int n_list = 0, n_list_cyl = 0;
-            if (cx.cull) n_list = item_list(cx, fl, make_beam<SRC>(__ldg(sc.bounds + f), src), f, n_list_cyl);
-            const float4* tab = sc.world + ((size_t)f * M) * 2;
-            SoftHexCache scache;
-            const bool soft7 = SENS == SENS_SOFT_HEX && MODE != MODE_DEBUG && sc.sens.ksize == 1;
-            if (soft7) scache.reset();
-            // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
-            const bool sub_beams = SUB && cx.cull && n_list >= 2 && n_list <= 32;   // one candidate: the test costs what it saves
-            const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
-            for (int mb = m0; mb < m1; mb += 32) {
-                const int m = mb + lane;
-                const bool live = m < m1;
-                const int mm = live ? m : m1 - 1;
-                const float4 a = __ldg(tab + 2 * mm), b = __ldg(tab + 2 * mm + 1);
-                unsigned sub_mask = 0xffffffffu;
-                if (SUB && sub_beams) {
-                    const Beam cb = make_beam<SRC>(__ldg(cbs + (mb >> 5)), src);
-                    sub_mask = __ballot_sync(0xffffffffu, lane < n_list && (!cb.ok || keep_primitive(cx.ob, cb, cx.list[lane])));
-                }
-                const size_t ri = ((size_t)f * plan.S + s) * M + __float_as_int(b.w);   // debug: original sample index
-                trace_ray<SRC, SENS, MODE, STAGES, SUB>(sc, cx, a, b, src, sval, live, n_list_cyl, n_list, sub_mask, ri, soft7,
-                                                        cache, scache, gout, out_val, out_pix);
-            }
-            if (SENS == SENS_SOFT_HEX && soft7) scache.flush(sc.sens, cx.lut, cx.hist);
-            __syncwarp();
+    if (MODE != MODE_MATRIX && queue.counter) {
+        const unsigned long long per_src = (unsigned long long)queue.runs * queue.msplit;
+        for (;;) {
+            unsigned long long u = 0;
+            if (lane == 0) u = atomicAdd(queue.counter, 1ull);
+            u = __shfl_sync(0xffffffffu, u, 0);
+            if (u >= (unsigned long long)queue.n_units) break;
+            const int s = (int)(u / per_src);
+            const int rem = (int)(u - (unsigned long long)s * per_src);
+            const int run = rem / queue.msplit, part = rem - run * queue.msplit;
+            const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
+            const float sval = __ldg(values + s);
+            const int f0 = run * queue.facets_per_unit, f1 = min(sc.F, f0 + queue.facets_per_unit);
+            const int m0 = part * queue.msize, m1 = min(M, m0 + queue.msize);
+            for (int f = f0; f < f1; ++f)
+                trace_item<SRC, SENS, MODE, STAGES, SUB>(sc, cx, fl, plan.S, s, src, sval, f, m0, m1, cache, out, out_val, out_pix);
         }
-        if (MODE == MODE_MATRIX && SENS != SENS_SQUARE) {
-            if (SENS == SENS_HEX) { cache.flush(cx.hist); cache.reset(); }
+    } else {
+        const bool pull = MODE == MODE_MATRIX && queue.counter != nullptr;
+        long long item = blockIdx.x;
+        int slot = 0;
+        if (pull) {
+            if (threadIdx.x == 0) s_item[0] = (long long)atomicAdd(queue.counter, 1ull);
             __syncthreads();
-            if (plan.n_chunks == 1) {
-                for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) { gout[i] = cx.hist[i]; cx.hist[i] = 0.f; }
-            } else {
-                for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) {
-                    const float v = cx.hist[i];
-                    if (v != 0.f) { atomicAdd(gout + i, v); cx.hist[i] = 0.f; }
+            item = s_item[0];
+        }
+        while (item < plan.n_items) {
+            const int s = (int)(item / plan.n_chunks), ch = (int)(item - (long long)s * plan.n_chunks);
+            const int f0 = ch * plan.chunk_facets, f1 = min(sc.F, f0 + plan.chunk_facets);
+            const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
+            const float sval = __ldg(values + s);
+            float* gout = MODE == MODE_MATRIX ? out + (size_t)s * npix : out;
+
+            const int n_w = (f1 - f0) * plan.msplit;
+            for (int wi = warp; wi < n_w; wi += nwarps) {
+                int fi = wi, part = 0;
+                if (plan.msplit > 1) { fi = wi / plan.msplit; part = wi - fi * plan.msplit; }
+                const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
+                trace_item<SRC, SENS, MODE, STAGES, SUB>(sc, cx, fl, plan.S, s, src, sval, f0 + fi, m0, m1, cache, gout, out_val, out_pix);
+            }
+            if (pull) {                                  // next item: slots alternate, so a slow reader never sees an overwrite
+                slot ^= 1;
+                if (threadIdx.x == 0) s_item[slot] = (long long)atomicAdd(queue.counter, 1ull);
+            }
+            if (MODE == MODE_MATRIX && SENS != SENS_SQUARE) {
+                if (SENS == SENS_HEX) { cache.flush(cx.hist); cache.reset(); }
+                __syncthreads();
+                if (plan.n_chunks == 1) {
+                    for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) { gout[i] = cx.hist[i]; cx.hist[i] = 0.f; }
+                } else {
+                    for (int i = threadIdx.x; i < sc.sens.npix; i += blockDim.x) {
+                        const float v = cx.hist[i];
+                        if (v != 0.f) { atomicAdd(gout + i, v); cx.hist[i] = 0.f; }
+                    }
                 }
             }
-            __syncthreads();
+            if (pull) { __syncthreads(); item = s_item[slot]; }
+            else {
+                if (MODE == MODE_MATRIX && SENS != SENS_SQUARE) __syncthreads();
+                item += gridDim.x;
+            }
         }
     }
     if (MODE == MODE_RENDER && SENS != SENS_SQUARE) {
@@ -483,7 +566,10 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const SensDev se, const
     }
 }
 
-template <typename K>
+#ifndef IACT_WORK_QUEUE
+#define IACT_WORK_QUEUE 1
+#endif
+template <int MODE, typename K>
 int launch_kernel(K kern, const SceneDev& d, const float* sources, const float* values, const LaunchPlan& plan, const FacetLists& fl,
                   float* out, float* out_val, int* out_pix, cudaStream_t stream, size_t smem) {
     const int threads = 256;
@@ -492,8 +578,18 @@ int launch_kernel(K kern, const SceneDev& d, const float* sources, const float* 
     IACT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
     if (occ < 1) occ = 1;
     const long long max_blocks = (long long)sm_count() * occ;
-    const unsigned grid = (unsigned)std::max(1LL, std::min(plan.n_items, max_blocks));
-    kern<<<grid, threads, smem, stream>>>(d, sources, values, plan, fl, out, out_val, out_pix);
+    QueuePlan q = make_queue_plan(d, plan.S, max_blocks * (threads / 32));
+    long long blocks = plan.n_items;
+    Scratch ctr;
+    if (IACT_WORK_QUEUE) {
+        int rc = ctr.alloc(sizeof(unsigned long long), stream);
+        if (rc) return rc;
+        IACT_CUDA(cudaMemsetAsync(ctr.ptr, 0, sizeof(unsigned long long), stream));
+        q.counter = reinterpret_cast<unsigned long long*>(ctr.ptr);
+        if (MODE != MODE_MATRIX) blocks = (q.n_units + threads / 32 - 1) / (threads / 32);
+    }
+    const unsigned grid = (unsigned)std::max(1LL, std::min(blocks, max_blocks));
+    kern<<<grid, threads, smem, stream>>>(d, sources, values, plan, q, fl, out, out_val, out_pix);
     iact_count_launch();
     return iact_check_cuda(cudaGetLastError(), "trace_kernel launch");
 }
@@ -504,8 +600,8 @@ int launch_variant(const SceneDev& d, const float* sources, const float* values,
     const int threads = 256;
     const size_t smem = smem_bytes(d, SENS, MODE, threads / 32);
     if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
-    if (d.chunk_bounds) return launch_kernel(trace_kernel<SRC, SENS, MODE, STAGES, true>, d, sources, values, plan, fl, out, out_val, out_pix, stream, smem);
-    return launch_kernel(trace_kernel<SRC, SENS, MODE, STAGES, false>, d, sources, values, plan, fl, out, out_val, out_pix, stream, smem);
+    if (d.chunk_bounds) return launch_kernel<MODE>(trace_kernel<SRC, SENS, MODE, STAGES, true>, d, sources, values, plan, fl, out, out_val, out_pix, stream, smem);
+    return launch_kernel<MODE>(trace_kernel<SRC, SENS, MODE, STAGES, false>, d, sources, values, plan, fl, out, out_val, out_pix, stream, smem);
 }
 
 #define ARGS const SceneDev& d, const float* a, const float* b, const LaunchPlan& p, const FacetLists& fl, float* o, float* ov, int* op, cudaStream_t st
