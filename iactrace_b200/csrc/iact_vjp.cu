@@ -15,6 +15,25 @@
 
 namespace {
 
+// Work queue of the VJP kernel: unit = (facet, sample part, run of `slen` consecutive sources).
+struct VjpPlan { int S, slen, sruns, msplit, msize; long long n_units; unsigned long long* counter; };
+
+VjpPlan make_vjp_plan(const SceneDev& d, int S, long long resident_warps) {
+    VjpPlan p;
+    p.S = S;
+    p.slen = (int)std::max(1LL, std::min(32LL, (long long)S * d.F / (resident_warps * 32)));
+    p.sruns = (S + p.slen - 1) / p.slen;
+    const long long base = (long long)d.F * p.sruns;
+    long long ms = 1;                                        // small jobs: split along the samples so every warp gets work
+    if (base < resident_warps * 4) ms = std::min<long long>((d.M + 31) / 32, (resident_warps * 4 + base - 1) / std::max(base, 1LL));
+    ms = std::max(ms, 1LL);
+    p.msize = (int)(((d.M + ms - 1) / ms + 31) / 32 * 32);
+    p.msplit = (d.M + p.msize - 1) / std::max(p.msize, 1);
+    p.n_units = base * p.msplit;
+    p.counter = nullptr;
+    return p;
+}
+
 struct GradsDev {
     float *weights, *values, *sources;
     float* facc;   // (F,13): dL/dR row-major (9), dL/dpos (3), dL/dscale (1)
@@ -246,7 +265,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <int SRC, int SENS, bool STAGES>
 __global__ void __launch_bounds__(256, STAGES ? IACT_VJP_MIN_BLOCKS_STAGES : IACT_VJP_MIN_BLOCKS)
 vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float* __restrict__ sources,
-           const float* __restrict__ values, const LaunchPlan plan, const FacetLists fl,
+           const float* __restrict__ values, const VjpPlan vp, const FacetLists fl,
            const float* __restrict__ G, const GradsDev gr) {
     extern __shared__ __align__(16) float smem[];
     ObsSmem ob;
@@ -274,36 +293,43 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
     // sensor adjoints accumulate per lane over the whole block lifetime
     V3 g_ps = v3(0.f, 0.f, 0.f), g_u1 = g_ps, g_u2 = g_ps, g_ns = g_ps;
 
-    for (long long item = blockIdx.x; item < plan.n_items; item += gridDim.x) {
-        const int s = (int)(item / plan.n_chunks), ch = (int)(item - (long long)s * plan.n_chunks);
-        const int f0 = ch * plan.chunk_facets, f1 = min(sc.F, f0 + plan.chunk_facets);
-        const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
-        const float sval = __ldg(values + s);
-        float g_val = 0.f;
-        V3 g_src = v3(0.f, 0.f, 0.f);
+    // Work queue: a unit = (facet, sample part, run of sources), pulled by one warp from a global counter.  The
+    // facet's pose is set up and its 13 adjoints are warp-reduced once per unit instead of once per (facet, source).
+    const bool per_source = gr.values != nullptr || gr.sources != nullptr;
+    for (;;) {
+        unsigned long long u = 0;
+        if (lane == 0) u = atomicAdd(vp.counter, 1ull);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= (unsigned long long)vp.n_units) break;
+        const int sr = (int)(u % (unsigned long long)vp.sruns);
+        const unsigned long long rest = u / (unsigned long long)vp.sruns;
+        const int part = (int)(rest % (unsigned long long)vp.msplit), f = (int)(rest / (unsigned long long)vp.msplit);
+        const int s0 = sr * vp.slen, s1 = min(vp.S, s0 + vp.slen);
+        const int m0 = part * vp.msize, m1 = min(M, m0 + vp.msize);
+        const M33 R = euler_to_matrix(__ldg(fa.rotations + 3 * f), __ldg(fa.rotations + 3 * f + 1), __ldg(fa.rotations + 3 * f + 2));
+        const V3 pos = ld3(fa.positions + 3 * f);
+        const float scale = __ldg(fa.scale + f);
+        const float4 bnd = __ldg(sc.bounds + f);
+        float gR[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        V3 g_pos = v3(0.f, 0.f, 0.f);
+        float g_scale = 0.f;
+        // stage >= 1 mirror adjoints: one register set per lane for the first stage's mirror 0..; rays
+        // that use another (stage, mirror) fall back to direct atomics
+        float mreg[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int mreg_id = -1;                                      // flat mirror id the register set belongs to
 
-        const int n_w = (f1 - f0) * plan.msplit;
-        for (int wi = warp; wi < n_w; wi += nwarps) {
-            const int fi = wi / plan.msplit, part = wi - fi * plan.msplit;
-            const int f = f0 + fi;
-            const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
+        for (int s = s0; s < s1; ++s) {
+            const V3 src = v3(__ldg(sources + 3 * s), __ldg(sources + 3 * s + 1), __ldg(sources + 3 * s + 2));
+            const float sval = __ldg(values + s);
+            float g_val = 0.f;
+            V3 g_src = v3(0.f, 0.f, 0.f);
             int n_list = 0, n_list_cyl = 0;
             if (cull) {
-                const Beam beam = make_beam<SRC>(__ldg(sc.bounds + f), src);
+                const Beam beam = make_beam<SRC>(bnd, src);
                 const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
                 if (cnt.x >= 0) n_list = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, n_list_cyl);
                 else            n_list = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, n_list_cyl);
             }
-            const M33 R = euler_to_matrix(__ldg(fa.rotations + 3 * f), __ldg(fa.rotations + 3 * f + 1), __ldg(fa.rotations + 3 * f + 2));
-            const V3 pos = ld3(fa.positions + 3 * f);
-            const float scale = __ldg(fa.scale + f);
-            float gR[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            V3 g_pos = v3(0.f, 0.f, 0.f);
-            float g_scale = 0.f;
-            // stage >= 1 mirror adjoints: one register set per lane for the first stage's mirror 0..; rays
-            // that use another (stage, mirror) fall back to direct atomics
-            float mreg[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            int mreg_id = -1;                                      // flat mirror id the register set belongs to
 
             for (int m = m0 + lane; m < m1; m += 32) {
                 const size_t li = ((size_t)f * M + m) * 3;
@@ -423,35 +449,37 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 gR[3] += g_o.y * pl.x + g_nw.y * nq.x; gR[4] += g_o.y * pl.y + g_nw.y * nq.y; gR[5] += g_o.y * pl.z + g_nw.y * nq.z;
                 gR[6] += g_o.z * pl.x + g_nw.z * nq.x; gR[7] += g_o.z * pl.y + g_nw.z * nq.y; gR[8] += g_o.z * pl.z + g_nw.z * nq.z;
             }
-            // per-facet adjoints: warp reduce, one atomic per component
-            float* acc = gr.facc + (size_t)f * 13;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) { const float v = warp_sum(gR[k]); if (lane == 0 && v != 0.f) atomicAdd(acc + k, v); }
-            { const float v = warp_sum(g_pos.x); if (lane == 0 && v != 0.f) atomicAdd(acc + 9, v); }
-            { const float v = warp_sum(g_pos.y); if (lane == 0 && v != 0.f) atomicAdd(acc + 10, v); }
-            { const float v = warp_sum(g_pos.z); if (lane == 0 && v != 0.f) atomicAdd(acc + 11, v); }
-            { const float v = warp_sum(g_scale); if (lane == 0 && v != 0.f) atomicAdd(acc + 12, v); }
-            if (STAGES && gr.macc) {
-                // lanes may have cached different mirrors: reduce per distinct id
-                unsigned todo = __ballot_sync(0xffffffffu, mreg_id >= 0);
-                while (todo) {
-                    const int id = __shfl_sync(0xffffffffu, mreg_id, __ffs(todo) - 1);
-                    const bool mine = mreg_id == id;
-#pragma unroll
-                    for (int q = 0; q < 12; ++q) { const float v = warp_sum(mine ? mreg[q] : 0.f); if (lane == 0 && v != 0.f) atomicAdd(gr.macc + (size_t)id * 12 + q, v); }
-                    todo &= ~__ballot_sync(0xffffffffu, mine);
+            // per-source adjoints
+            if (per_source) {
+                g_val = warp_sum(g_val); g_src.x = warp_sum(g_src.x); g_src.y = warp_sum(g_src.y); g_src.z = warp_sum(g_src.z);
+                if (lane == 0) {
+                    if (gr.values && g_val != 0.f) atomicAdd(gr.values + s, g_val);
+                    if (gr.sources) {
+                        if (g_src.x != 0.f) atomicAdd(gr.sources + 3 * s, g_src.x);
+                        if (g_src.y != 0.f) atomicAdd(gr.sources + 3 * s + 1, g_src.y);
+                        if (g_src.z != 0.f) atomicAdd(gr.sources + 3 * s + 2, g_src.z);
+                    }
                 }
             }
-            __syncwarp();
+            __syncwarp();                                          // the list is rebuilt for the next source
         }
-        // per-source adjoints
-        g_val = warp_sum(g_val); g_src.x = warp_sum(g_src.x); g_src.y = warp_sum(g_src.y); g_src.z = warp_sum(g_src.z);
-        if (lane == 0) {
-            if (gr.values && g_val != 0.f) atomicAdd(gr.values + s, g_val);
-            if (gr.sources) {
-                if (g_src.x != 0.f) atomicAdd(gr.sources + 3 * s, g_src.x);
-                if (g_src.y != 0.f) atomicAdd(gr.sources + 3 * s + 1, g_src.y);
-                if (g_src.z != 0.f) atomicAdd(gr.sources + 3 * s + 2, g_src.z);
+        // per-facet adjoints: warp reduce, one atomic per component
+        float* acc = gr.facc + (size_t)f * 13;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const float v = warp_sum(gR[k]); if (lane == 0 && v != 0.f) atomicAdd(acc + k, v); }
+        { const float v = warp_sum(g_pos.x); if (lane == 0 && v != 0.f) atomicAdd(acc + 9, v); }
+        { const float v = warp_sum(g_pos.y); if (lane == 0 && v != 0.f) atomicAdd(acc + 10, v); }
+        { const float v = warp_sum(g_pos.z); if (lane == 0 && v != 0.f) atomicAdd(acc + 11, v); }
+        { const float v = warp_sum(g_scale); if (lane == 0 && v != 0.f) atomicAdd(acc + 12, v); }
+        if (STAGES && gr.macc) {
+            // lanes may have cached different mirrors: reduce per distinct id
+            unsigned todo = __ballot_sync(0xffffffffu, mreg_id >= 0);
+            while (todo) {
+                const int id = __shfl_sync(0xffffffffu, mreg_id, __ffs(todo) - 1);
+                const bool mine = mreg_id == id;
+#pragma unroll
+                for (int q = 0; q < 12; ++q) { const float v = warp_sum(mine ? mreg[q] : 0.f); if (lane == 0 && v != 0.f) atomicAdd(gr.macc + (size_t)id * 12 + q, v); }
+                todo &= ~__ballot_sync(0xffffffffu, mine);
             }
         }
     }
@@ -536,7 +564,6 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
                  "null facet table");
     cudaStream_t st = (cudaStream_t)stream;
     const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
-    LaunchPlan plan = make_plan(d, S, MODE_RENDER);
     Scratch cull_scr, acc_scr;
     FacetLists fl;
     fl.ids = nullptr; fl.count = nullptr; fl.stride = 0;
@@ -544,13 +571,14 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     int n2 = 0;
     for (int k = 0; k < d.n_stages; ++k) n2 += d.stages[k].n;
     const bool want_stage = n2 > 0 && (grads->stage_positions || grads->stage_rotations);
-    const size_t acc_floats = (size_t)d.F * 13 + 12 + (want_stage ? (size_t)n2 * 12 : 0);
+    // scratch: the work-queue counter (8 bytes) followed by the adjoint accumulators
+    const size_t acc_floats = 2 + (size_t)d.F * 13 + 12 + (want_stage ? (size_t)n2 * 12 : 0);
     rc = acc_scr.alloc(acc_floats * sizeof(float), st);
     if (rc) return rc;
     IACT_CUDA(cudaMemsetAsync(acc_scr.ptr, 0, acc_floats * sizeof(float), st));
     GradsDev gr;
     gr.weights = grads->weights; gr.values = grads->values; gr.sources = grads->sources;
-    gr.facc = reinterpret_cast<float*>(acc_scr.ptr);
+    gr.facc = reinterpret_cast<float*>(acc_scr.ptr) + 2;
     gr.sacc = gr.facc + (size_t)d.F * 13;
     gr.macc = want_stage ? gr.sacc + 12 : nullptr;
 
@@ -565,8 +593,11 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
         int occ = 0;
         IACT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
         const long long max_blocks = (long long)sm_count() * std::max(occ, 1);
-        const unsigned grid = (unsigned)std::max(1LL, std::min(plan.n_items, max_blocks));
-        kern<<<grid, threads, smem, st>>>(d, *facets, sources, values, plan, fl, cotangent, gr);
+        VjpPlan vp = make_vjp_plan(d, S, max_blocks * (threads / 32));
+        vp.counter = reinterpret_cast<unsigned long long*>(acc_scr.ptr);
+        const long long blocks = (vp.n_units + threads / 32 - 1) / (threads / 32);
+        const unsigned grid = (unsigned)std::max(1LL, std::min(blocks, max_blocks));
+        kern<<<grid, threads, smem, st>>>(d, *facets, sources, values, vp, fl, cotangent, gr);
         iact_count_launch();
         return iact_check_cuda(cudaGetLastError(), "vjp_kernel launch");
     };
