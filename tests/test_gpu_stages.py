@@ -7,6 +7,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 import iactrace_b200 as I
+from iactrace_b200 import config as Rm
 from iactrace_b200.core import (Box, Cylinder, OrientedBox, Sphere, Triangle, group_obstructions, render,
                                 render_debug)
 from iactrace_b200.io import build_telescope, load_packed_config
@@ -78,6 +79,47 @@ def test_all_obstruction_primitives():
         assert 0.005 < frac < 0.9, (name, frac)
         assert flips.mean() < 3e-4, (name, flips.sum())
         np.testing.assert_allclose(v[~flips], ov[~flips], rtol=1e-5, atol=0)
+
+
+def test_cylinder_caps_axis_parallel_rays_and_origins_inside():
+    """The interval form of the cylinder test (csrc/iact_trace.cuh hit_cylinder) against the oracle's literal
+    candidate tests (intersections.py:44-87): cap hits, rays parallel / nearly parallel to the axis (literal
+    fallback below 1.8 deg), rays at moderate angles, and ray origins inside a cylinder."""
+    cfg = subset_config(load_packed_config("CT3"), mirror_step=3)
+    cfg = dict(cfg, obstructions=[])
+    base = build_telescope(cfg, I.MCIntegrator(96), I.random.key(11))
+    plist = [
+        Cylinder([0.5, 0.5, 4.0], [0.5, 0.5, 6.0], 0.8),        # axis along z: on-axis rays run parallel to it, hit its caps
+        Cylinder([-2.0, 1.0, 5.0], [-2.0, 1.0, 5.05], 1.2),     # flat disc: almost only cap hits
+        Cylinder([3.0, -2.5, 3.0], [2.0, -1.5, 9.0], 0.5),      # inclined strut
+        Cylinder([-3.5, -3.0, -1.0], [-3.5, -3.0, 3.0], 1.0),   # swallows some facets: ray origins inside the solid
+        Cylinder([1.0, -4.0, 2.0], [1.05, -4.0, 8.0], 0.3),     # 0.5 deg off the z axis
+    ]
+    tel = I.Telescope(base.mirror_groups, group_obstructions(plist), base.sensors)
+    ang = np.deg2rad([0.0, 0.5, 1.5, 2.5, 8.0, 25.0])
+    src = np.stack([-np.sin(ang), np.zeros_like(ang), -np.cos(ang)], axis=1).astype(np.float32)
+    val = np.ones(len(src), np.float32)
+    for cull in (True, False):
+        Rm.cull_obstructions = cull
+        try:
+            xy, v = render_debug(tel, src, val, "parallel", 1)
+        finally:
+            Rm.cull_obstructions = True
+        v = v.cpu().numpy()
+        _, ov = otrace.render_debug(to_oracle_scene(tel), src, val, "parallel", 1, np.float64)
+        flips = (v != 0) != (ov != 0)
+        frac = (ov == 0).mean()
+        assert 0.02 < frac < 0.9, frac
+        assert flips.mean() < 3e-4, (cull, flips.sum())
+        np.testing.assert_allclose(v[~flips], ov[~flips], rtol=1e-5, atol=0)
+    # point sources a few metres away: wide range of ray/axis angles within one beam
+    psrc = np.array([[0.5, 0.5, 30.0], [6.0, -3.0, 12.0], [-2.0, 1.0, 20.0]], np.float32)
+    _, v = render_debug(tel, psrc, np.ones(3, np.float32), "point", 1)
+    _, ov = otrace.render_debug(to_oracle_scene(tel), psrc, np.ones(3, np.float32), "point", 1, np.float64)
+    v = v.cpu().numpy()
+    flips = (v != 0) != (ov != 0)
+    assert flips.mean() < 3e-4, flips.sum()
+    np.testing.assert_allclose(v[~flips], ov[~flips], rtol=1e-5, atol=0)
 
 
 def test_soft_sensors_forward():
