@@ -1,4 +1,5 @@
 """Runtime switches of the CUDA path (process-wide)."""
+import os as _os
 
 # Conservative beam/obstruction culling in the trace kernel.  Culling never changes a ray's result
 # (tests/test_gpu_trace.py::test_culling_is_exact compares every ray against brute force); turning
@@ -11,8 +12,9 @@ return_numpy = False
 
 # From this many samples per facet on, the world table is written in spatially binned order
 # (iact_transform_to_world_binned) and the trace kernel culls again per 32-sample run.  Below it the
-# per-iteration test costs more than it saves.  0 disables binning.
-bin_samples_min = 256
-# ... and only for scenes with at least this many obstruction primitives: with few of them the
-# candidate lists are mostly empty and the per-run test does not pay (CT3: 33 cylinders, -5 %).
-bin_obstructions_min = 100
+# runs are too large a part of the facet to shed candidates (CT5, M = 115: 1.56 -> 1.20 cylinder tests per
+# ray, 4.7 -> 5.2 ms).  0 disables binning.  The environment overrides are for tuning runs.
+bin_samples_min = int(_os.environ.get("IACTRACE_B200_BIN_SAMPLES_MIN", "256"))
+# ... and only for scenes with at least this many obstruction primitives: with a handful of them the
+# candidate lists are mostly empty.  (CT3, 33 cylinders, M = 1000: 12.9 -> 11.8 ms with the strip test.)
+bin_obstructions_min = int(_os.environ.get("IACTRACE_B200_BIN_OBSTRUCTIONS_MIN", "16"))

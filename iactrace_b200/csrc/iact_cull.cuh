@@ -67,6 +67,46 @@ __device__ __forceinline__ bool keep_primitive(const ObsSmem& ob, const Beam& b,
     return beam_keeps_capsule(b, v3(c[id], c[n + id], c[2 * n + id]), v3(c[3 * n + id], c[4 * n + id], c[5 * n + id]), c[6 * n + id]);
 }
 
+// Level-3 strip test (far or parallel sources, parallax R/D < 1e-7): the rays of a (facet, source) item are
+// parallel to the beam axis u, so a ray can touch cylinder e only if its origin lies within r_e of the plane
+// through the cylinder axis that contains u: |n_e.(o - p1_e)| <= r_e with n_e = unit(u x axis_e).  A run of 32
+// table rows with bounding sphere (c, R) therefore needs cylinder e only if |n_e.c - n_e.p1_e| <= R + r_e + margins
+// (2 mm + 1e-5 t for float32 rounding plus the parallax term, as in beam_keeps_capsule; the residual tilt of a
+// ray against u, <= 2e-7, moves it by < 0.1 mm over the 50 m of a telescope).  Cylinders within 3 deg of the
+// beam axis (n_e ill-conditioned) and the other primitive types are always kept.
+// strip_masks: lane j returns the keep mask (bit e = list entry e) of run run0 + j; the candidates' records are
+// computed by lane e and broadcast by shuffles, about 10 instructions per candidate for 32 runs.
+__device__ __forceinline__ bool strip_applies(const Beam& b) { return b.ok && b.R * b.invD < 1e-7f; }
+__device__ __forceinline__ unsigned strip_masks(const ObsSmem& ob, const Beam& beam, const unsigned short* list, int n_list_cyl,
+                                                int n_list, const float4* __restrict__ cbs, int n_runs, int run0) {
+    const int lane = threadIdx.x & 31;
+    V3 sn = v3(0.f, 0.f, 0.f);
+    float sk = 0.f, srr = INFINITY;                                         // INFINITY = always kept
+    if (lane < n_list_cyl) {
+        const float* c = ob.cprox; const int n = ob.n_cyl + ob.n_rest; const int id = list[lane];
+        const V3 p1 = v3(c[id], c[n + id], c[2 * n + id]), p2 = v3(c[3 * n + id], c[4 * n + id], c[5 * n + id]);
+        const float r = c[6 * n + id];
+        const V3 ax = p2 - p1;
+        const V3 w = cross(beam.u, ax);
+        const float w2 = dot(w, w), a2 = dot(ax, ax);
+        if (w2 >= 2.5e-3f * a2 && a2 > 1e-20f) {
+            sn = rsqrtf(w2) * w;
+            sk = dot(sn, p1);
+            const float tfar = 1.1f * (fmaxf(fmaxf(dot(p1 - beam.c, beam.u), dot(p2 - beam.c, beam.u)), 0.f) + r + beam.R);
+            srr = r + 2e-3f + 1e-5f * tfar + beam.R * 1.5708f * tfar * beam.invD;
+        }
+    }
+    const float4 cb = __ldg(cbs + min(run0 + lane, n_runs - 1));
+    unsigned mask = 0u;
+    for (int e = 0; e < n_list; ++e) {
+        const float nx = __shfl_sync(0xffffffffu, sn.x, e), ny = __shfl_sync(0xffffffffu, sn.y, e), nz = __shfl_sync(0xffffffffu, sn.z, e);
+        const float k = __shfl_sync(0xffffffffu, sk, e), rr = __shfl_sync(0xffffffffu, srr, e);
+        const float sd = nx * cb.x + ny * cb.y + nz * cb.z - k;
+        if (!(fabsf(sd) > cb.w + rr)) mask |= 1u << e;
+    }
+    return mask;
+}
+
 // Warp-cooperative compaction of the primitives a beam can reach.  `cand` (may be null = all
 // primitives) lists candidate ids, cylinders first (n_cand_cyl of n_cand).  Writes ids to `out`
 // (shared or global), returns the total and sets n_cyl_out.  Order is preserved.

@@ -390,14 +390,28 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
     const int lane = threadIdx.x & 31;
     const int M = sc.M;
     int n_list = 0, n_list_cyl = 0;
-    if (cx.cull) n_list = item_list(cx, fl, make_beam<SRC>(__ldg(sc.bounds + f), src), f, n_list_cyl);
+    Beam beam;
+    beam.ok = false;
+    if (cx.cull) {
+        beam = make_beam<SRC>(__ldg(sc.bounds + f), src);
+        n_list = item_list(cx, fl, beam, f, n_list_cyl);
+    }
     const float4* tab = sc.world + ((size_t)f * M) * 2;
     SoftHexCache scache;
     const bool soft7 = SENS == SENS_SOFT_HEX && MODE != MODE_DEBUG && sc.sens.ksize == 1;
     if (soft7) scache.reset();
     // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
-    const bool sub_beams = SUB && cx.cull && n_list >= 2 && n_list <= 32;   // one candidate: the test costs what it saves
+    const bool sub_beams = SUB && cx.cull && n_list >= 1 && n_list <= 32;
     const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
+    // far or parallel sources: strip test, the masks of 32 consecutive runs at once (iact_cull.cuh strip_masks), so
+    // nothing but one mask word per lane stays live across the ray loop; nearer sources: capsule test per run
+    const bool strip = SUB && sub_beams && strip_applies(beam);
+    auto run_strip_masks = [&](int run0) -> unsigned {
+        const Beam b = make_beam<SRC>(__ldg(sc.bounds + f), src);           // recomputed: nothing of it stays live in the ray loop
+        return strip_masks(cx.ob, b, cx.list, n_list_cyl, n_list, sc.chunk_bounds + (size_t)f * ((M + 31) >> 5), (M + 31) >> 5, run0);
+    };
+    unsigned run_masks = 0xffffffffu;                                        // lane j: run ((mb >> 5) & ~31) + j
+    if (SUB && strip) run_masks = run_strip_masks((m0 >> 5) & ~31);
     for (int mb = m0; mb < m1; mb += 32) {
         const int m = mb + lane;
         const bool live = m < m1;
@@ -405,8 +419,13 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
         const float4 a = __ldg(tab + 2 * mm), b = __ldg(tab + 2 * mm + 1);
         unsigned sub_mask = 0xffffffffu;
         if (SUB && sub_beams) {
-            const Beam cb = make_beam<SRC>(__ldg(cbs + (mb >> 5)), src);
-            sub_mask = __ballot_sync(0xffffffffu, lane < n_list && (!cb.ok || keep_primitive(cx.ob, cb, cx.list[lane])));
+            if (strip) {
+                if (((mb >> 5) & 31) == 0 && mb != m0) run_masks = run_strip_masks(mb >> 5);
+                sub_mask = __shfl_sync(0xffffffffu, run_masks, (mb >> 5) & 31);
+            } else {
+                const Beam cb = make_beam<SRC>(__ldg(cbs + (mb >> 5)), src);
+                sub_mask = __ballot_sync(0xffffffffu, lane < n_list && (!cb.ok || keep_primitive(cx.ob, cb, cx.list[lane])));
+            }
         }
         const size_t ri = ((size_t)f * S + s) * M + __float_as_int(b.w);   // debug: original sample index
         trace_ray<SRC, SENS, MODE, STAGES, SUB>(sc, cx, a, b, src, sval, live, n_list_cyl, n_list, sub_mask, ri, soft7,
@@ -534,12 +553,20 @@ __global__ void __launch_bounds__(256) cull_stats_kernel(const __grid_constant__
         int ncyl = 0, n;
         if (cnt.x >= 0) n = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, ncyl);
         else            n = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, ncyl);
-        if (sc.chunk_bounds && n >= 2 && n <= 32) {
+        if (sc.chunk_bounds && n >= 1 && n <= 32) {
             // level 3: what each 32-row run actually tests (same rule as trace_kernel<..., SUB = true>)
+            const bool strip = strip_applies(beam);
+            unsigned masks = 0u;
             for (int k = 0; k < n_chunks; ++k) {
-                const Beam cb = make_beam<SRC>(__ldg(sc.chunk_bounds + (size_t)f * n_chunks + k), src);
-                const unsigned mask = __ballot_sync(0xffffffffu, lane < n && (!cb.ok || keep_primitive(ob, cb, list[lane])));
-                const unsigned mc = mask & ((1u << ncyl) - 1u);
+                unsigned mask;
+                if (strip) {
+                    if ((k & 31) == 0) masks = strip_masks(ob, beam, list, ncyl, n, sc.chunk_bounds + (size_t)f * n_chunks, n_chunks, k);
+                    mask = __shfl_sync(0xffffffffu, masks, k & 31);
+                } else {
+                    const Beam cb = make_beam<SRC>(__ldg(sc.chunk_bounds + (size_t)f * n_chunks + k), src);
+                    mask = __ballot_sync(0xffffffffu, lane < n && (!cb.ok || keep_primitive(ob, cb, list[lane])));
+                }
+                const unsigned mc = ncyl >= 32 ? mask : (mask & ((1u << ncyl) - 1u));
                 const int rays = min(32, M - 32 * k);
                 a += (unsigned long long)__popc(mc) * rays; b += (unsigned long long)__popc(mask & ~mc) * rays;
             }
