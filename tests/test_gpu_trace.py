@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 
 import iactrace_b200 as I
 from iactrace_b200 import config as Rm
+_BIN_DEFAULTS = (Rm.bin_samples_min, Rm.bin_obstructions_min)
 from iactrace_b200.core import render, render_debug, render_response_matrix
 from iactrace_b200.io import build_telescope, load_packed_config
 from oracle import trace as otrace
@@ -186,7 +187,7 @@ def test_binned_table_and_sub_beam_culling_are_exact():
                 img = render(tel, src, val, stype, 0)
                 out[name] = (xy.cpu().numpy(), v.cpu().numpy(), pix.cpu().numpy(), img.cpu().numpy())
             finally:
-                Rm.cull_obstructions, Rm.bin_samples_min, Rm.bin_obstructions_min = True, 256, 100
+                Rm.cull_obstructions, Rm.bin_samples_min, Rm.bin_obstructions_min = (True,) + _BIN_DEFAULTS
         ref = out["plain+culled"]
         for name in ("binned+culled", "binned brute force"):
             for a, b in zip(out[name][:3], ref[:3]):
@@ -233,7 +234,7 @@ def test_long_candidate_lists_and_table_limits():
             xy, v = render_debug(tel, src, val, "point", 0)
             res.append((xy.cpu().numpy(), v.cpu().numpy()))
         finally:
-            Rm.cull_obstructions, Rm.bin_obstructions_min = True, 100
+            Rm.cull_obstructions, Rm.bin_obstructions_min = True, _BIN_DEFAULTS[1]
     for r in res[1:]:
         assert np.array_equal(r[1], res[0][1]) and np.array_equal(r[0], res[0][0])
     assert 0.005 < (res[0][1] == 0).mean() < 0.5
