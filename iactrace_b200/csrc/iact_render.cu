@@ -376,10 +376,11 @@ __device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx
 
 // Level-2 candidate list of one beam into the warp's shared-memory list.
 __device__ __forceinline__ int item_list(const TraceCtx& cx, const FacetLists& fl, const Beam& beam, int f, int& n_list_cyl) {
+    unsigned short* out = cx.list;
     const int n_obs = cx.ob.n_cyl + cx.ob.n_rest;
     const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
-    if (cnt.x >= 0) return build_list(cx.ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, cx.list, n_list_cyl);
-    return build_list(cx.ob, beam, (const unsigned short*)nullptr, cx.ob.n_cyl, n_obs, cx.list, n_list_cyl);
+    if (cnt.x >= 0) return build_list(cx.ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, out, n_list_cyl);
+    return build_list(cx.ob, beam, (const unsigned short*)nullptr, cx.ob.n_cyl, n_obs, out, n_list_cyl);
 }
 
 // One warp item: rays m0..m1 of facet f seen from source s (level-2 list, optional level-3 masks, per-ray trace).
@@ -439,7 +440,7 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
 // global counter (QueuePlan), so no warp idles while another still has a backlog -- with the static
 // grid-stride split 18 % of the resident warp slots were empty (blocks and warps of unequal cost finishing
 // early).  Response matrix: one block owns a source row (its histogram is the row), so whole block items are
-// pulled from the same counter.  queue.counter == nullptr selects the static split.
+// pulled from the same counter (queue.counter == nullptr there selects a static grid-stride split).
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
 __global__ void __launch_bounds__(256, STAGES ? IACT_MIN_BLOCKS_STAGES : IACT_MIN_BLOCKS)
 trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
@@ -457,7 +458,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     PixCache cache;
     cache.reset();
 
-    if (MODE != MODE_MATRIX && queue.counter) {
+    if (MODE != MODE_MATRIX) {                    // compile-time: render / debug kernels hold the queue path only (code size)
         const unsigned long long per_src = (unsigned long long)queue.runs * queue.msplit;
         for (;;) {
             unsigned long long u = 0;
@@ -593,9 +594,6 @@ __global__ void __launch_bounds__(256) accumulate_kernel(const SensDev se, const
     }
 }
 
-#ifndef IACT_WORK_QUEUE
-#define IACT_WORK_QUEUE 1
-#endif
 template <int MODE, typename K>
 int launch_kernel(K kern, const SceneDev& d, const float* sources, const float* values, const LaunchPlan& plan, const FacetLists& fl,
                   float* out, float* out_val, int* out_pix, cudaStream_t stream, size_t smem) {
@@ -608,7 +606,7 @@ int launch_kernel(K kern, const SceneDev& d, const float* sources, const float* 
     QueuePlan q = make_queue_plan(d, plan.S, max_blocks * (threads / 32));
     long long blocks = plan.n_items;
     Scratch ctr;
-    if (IACT_WORK_QUEUE) {
+    {
         int rc = ctr.alloc(sizeof(unsigned long long), stream);
         if (rc) return rc;
         IACT_CUDA(cudaMemsetAsync(ctr.ptr, 0, sizeof(unsigned long long), stream));
