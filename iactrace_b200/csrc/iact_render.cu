@@ -38,7 +38,7 @@ __device__ __forceinline__ void splat_soft_hex(const SensDev& se, const LUT* lut
                 const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
                 const float hd = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) * se.inv_inradius;
                 const float z = hd * inv_sigma;
-                const float w = expf(-0.5f * z * z);
+                const float w = gauss_half(z * z);
                 if (pass == 0) { wsum += w; continue; }
                 const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
                 if (pix >= 0) atomicAdd(hist + pix, val * (w / wsum));
@@ -59,7 +59,7 @@ __device__ __forceinline__ void splat_soft_square(const SensDev& se, float x, fl
         for (int oy = -K; oy <= K; ++oy)
             for (int ox = -K; ox <= K; ++ox) {
                 const float dx = fx - (float)ox, dy = fy - (float)oy;
-                const float w = expf(-0.5f * (dx * dx + dy * dy) * inv_s2);
+                const float w = gauss_half((dx * dx + dy * dy) * inv_s2);
                 if (pass == 0) { wsum += w; continue; }
                 const int xi = (int)xb + ox, yi = (int)yb + oy;
                 if (xi >= 0 && xi < se.W && yi >= 0 && yi < se.H) atomicAdd(img + (size_t)yi * se.W + xi, val * (w / wsum));
@@ -110,7 +110,7 @@ __device__ __forceinline__ void splat_soft_hex_warp(const SensDev& se, const LUT
             const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
             const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
             const float z = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) * se.inv_inradius * inv_sigma;
-            wsum += expf(-0.5f * z * z);
+            wsum += gauss_half(z * z);
         }
     const float scale = active ? val / wsum : 0.f;
     for (int oq = -K; oq <= K; ++oq)
@@ -119,7 +119,7 @@ __device__ __forceinline__ void splat_soft_hex_warp(const SensDev& se, const LUT
             const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
             const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
             const float z = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) * se.inv_inradius * inv_sigma;
-            const float w = expf(-0.5f * z * z);
+            const float w = gauss_half(z * z);
             const int pix = active ? hex_lookup(se, lut, qb + (float)oq, rb + (float)orr) : -1;
             warp_hist_add(hist, pix, scale * w);
         }
@@ -159,7 +159,7 @@ struct SoftHexCache {
                 const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
                 const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
                 const float z = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) * se.inv_inradius * inv_sigma;
-                w[t] = expf(-0.5f * z * z); wsum += w[t]; ++t;
+                w[t] = gauss_half(z * z); wsum += w[t]; ++t;
             }
         const float scale = active ? val / wsum : 0.f;
         const bool cached = active && qb == qb0 && rb == rb0;

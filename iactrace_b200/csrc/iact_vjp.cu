@@ -70,7 +70,7 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
         for (int oy = -K; oy <= K; ++oy)
             for (int ox = -K; ox <= K; ++ox) {
                 const float ddx = fx - (float)ox, ddy = fy - (float)oy;
-                const float w = expf(-0.5f * (ddx * ddx + ddy * ddy) * inv_s2);
+                const float w = gauss_half((ddx * ddx + ddy * ddy) * inv_s2);
                 const float dwx = -w * ddx * inv_s2, dwy = -w * ddy * inv_s2;
                 const int xi = (int)xb + ox, yi = (int)yb + oy;
                 const float g = (xi >= 0 && xi < se.W && yi >= 0 && yi < se.H) ? __ldg(G + (size_t)yi * se.W + xi) : 0.f;
@@ -98,7 +98,7 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
         const float alt = 0.5f * aa + 0.8660254037844386f * ab;
         const bool first = aa >= alt;
         const float z = fmaxf(aa, alt) * se.inv_inradius * inv_sigma;
-        const float w = expf(-0.5f * z * z);
+        const float w = gauss_half(z * z);
         // d hd / d a, d hd / d b  (sign(0) = 0, as jnp.abs)
         const float sa = a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f), sb = b > 0.f ? 1.f : (b < 0.f ? -1.f : 0.f);
         const float dha = (first ? sa : 0.5f * sa) * se.inv_inradius;
