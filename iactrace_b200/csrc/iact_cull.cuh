@@ -397,10 +397,16 @@ LaunchPlan make_plan(const SceneDev& d, int S, int mode) {
 
 // Units of the render / debug work queue: about 64 per resident warp when the job is large (short tail, one
 // atomic per ~1e4 warp instructions); small jobs are split along the samples so that every warp gets work.
+#ifndef IACT_QUEUE_FPU
+#define IACT_QUEUE_FPU 8
+#endif
+#ifndef IACT_QUEUE_UNITS
+#define IACT_QUEUE_UNITS 64
+#endif
 QueuePlan make_queue_plan(const SceneDev& d, int S, long long resident_warps) {
     QueuePlan q;
     const long long pairs = (long long)S * d.F;
-    q.facets_per_unit = (int)std::max(1LL, std::min(8LL, pairs / (resident_warps * 64)));
+    q.facets_per_unit = (int)std::max(1LL, std::min((long long)IACT_QUEUE_FPU, pairs / (resident_warps * IACT_QUEUE_UNITS)));
     q.runs = (d.F + q.facets_per_unit - 1) / q.facets_per_unit;
     const long long base = (long long)S * q.runs;
     long long ms = 1;
