@@ -63,3 +63,63 @@ def test_config4_ct3_response_matrix_properties():
     assert float(area[0, 0]) == 0.0 and float(area[-1, -1]) == 0.0
     # per-pixel response peaks at a sizeable fraction of the dish (cell 19: ~66 m^2 for pixel 42)
     assert 30.0 < float(M.max()) < 105.0
+
+
+def test_config3_cassegrain_1e9_rays_properties():
+    """Config 3: Cassegrain (secondary mirror) + cylinder/box/sphere obstructions, 10 000 parallel directions x
+    6 segments x 16 667 samples = 1.0e9 rays on the 1024^2 sensor."""
+    from iactrace_b200.workloads import cassegrain_config, star_field
+    tel = build_telescope(cassegrain_config(True), I.MCIntegrator(16667), I.random.key(0))
+    d, flux = star_field(10000, 3.0)
+    src, val = torch.from_numpy(d).cuda(), torch.from_numpy(flux).cuda()
+    full = render(tel, src, val, "parallel", 0)
+    assert full.shape == (1024, 1024) and torch.isfinite(full).all() and float(full.min()) >= 0.0
+    # a star puts its 1e5 rays into a dozen pixels by per-ray float32 atomics in launch-dependent order: the sum of
+    # 1e4-1e5 addends carries a few 1e-4 of relative rounding noise (the reference's float32 segment_sum does too)
+    tol = dict(rtol=1e-3, atol=5e-6 * float(full.max()))
+    # additivity over a partition of the directions, linearity in the fluxes
+    a = render(tel, src[:3000], val[:3000], "parallel", 0)
+    b = render(tel, src[3000:], val[3000:], "parallel", 0)
+    torch.testing.assert_close(a + b, full, **tol)
+    torch.testing.assert_close(render(tel, src, 2.0 * val, "parallel", 0), 2.0 * full, **tol)
+    # the obstructions only remove light; the spider in front of the secondary shadows a few per cent
+    clear = render(tel.clear_obstructions(), src, val, "parallel", 0)
+    frac = 1.0 - float(full.sum()) / float(clear.sum())
+    assert 0.0 < frac < 0.3, frac
+    # an on-axis star is imaged to a spot at the sensor centre (paraboloid + hyperboloid: stigmatic on axis)
+    star = render(tel, torch.tensor([[0.0, 0.0, -1.0]], device="cuda"), torch.ones(1, device="cuda"), "parallel", 0)
+    iy, ix = np.unravel_index(int(star.argmax()), star.shape)
+    assert abs(iy - 512) <= 2 and abs(ix - 512) <= 2
+    assert float(star[iy - 3:iy + 4, ix - 3:ix + 4].sum()) > 0.9 * float(star.sum())
+
+
+def test_config5_ct5_alignment_gradient_directional_derivative(ct5):
+    """Config 5 at full size: CT5 with the soft hex camera, 4096 sources x 876 x 115 rays; the kernel's gradient of
+    1/2 |img(theta) - img(theta*)|^2 w.r.t. the 876 x 3 facet rotations against a central finite difference of the
+    loss along a random tip/tilt direction."""
+    from iactrace_b200._util import replace
+    from iactrace_b200.sensors import DifferentiableHexagonalSensor
+    hard = ct5.sensors[0]
+    tel = ct5.replace_sensor(DifferentiableHexagonalSensor(hard.position, hard.rotation, hard.hex_centers, 0.5, 1,
+                                                           grid=hard.grid_constants()), 0)
+    src = torch.from_numpy(point_grid(64, 1.5)).cuda()
+    val = torch.ones(4096, device="cuda")
+    target = render(tel.apply_misalignment_to_group(0, 15, 10, I.random.key(4242)), src, val, "point", 0)
+    g = tel.mirror_groups[0]
+
+    def loss_of(r):
+        t = replace(tel, mirror_groups=[replace(g, rotations=r)])
+        return 0.5 * ((render(t, src, val, "point", 0).double() - target.double()) ** 2).sum()
+
+    rot = g.rotations.detach().clone().requires_grad_(True)
+    loss_of(rot).backward()
+    grad = rot.grad.double()
+    assert grad.shape == (876, 3) and torch.isfinite(grad).all()
+    v = torch.zeros_like(grad)
+    v[:, :2] = torch.randn(876, 2, device="cuda", dtype=torch.float64, generator=torch.Generator(device="cuda").manual_seed(3))
+    eps = 2e-4                                                # degrees: 0.7 arcsec, well inside the Gaussian taps' linear range
+    with torch.no_grad():
+        base = g.rotations.detach()
+        fd = (loss_of((base.double() + eps * v).float()) - loss_of((base.double() - eps * v).float())) / (2 * eps)
+    want = float((grad * v).sum())
+    assert abs(float(fd) - want) <= 0.05 * abs(want) + 1e-3 * float(grad.abs().max()), (float(fd), want)
