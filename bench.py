@@ -235,6 +235,9 @@ def main():
             dist.all_reduce(img)
         return img
 
+    out_host = []                                   # pinned result buffer, allocated once (a pageable .cpu() copy of the
+                                                    # 15.7 MB / 1 GB response matrices runs at a tenth of the PCIe rate)
+
     def step_e2e():
         s = src_host.to(dev, non_blocking=True)
         v = val_host.to(dev, non_blocking=True)
@@ -244,7 +247,11 @@ def main():
             out = render_fn(tel, s, v, stype, w["sensor"])
             if world > 1:
                 dist.all_reduce(out)
-        return out.cpu()
+        if not out_host:
+            out_host.append(torch.empty(out.shape, dtype=out.dtype, pin_memory=True))
+        out_host[0].copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()   # the step's result is on the host before the next step starts
+        return out_host[0]
 
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
