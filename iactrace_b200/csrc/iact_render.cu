@@ -262,6 +262,9 @@ struct PixCache {
 #ifndef IACT_MIN_BLOCKS
 #define IACT_MIN_BLOCKS 4
 #endif
+#ifndef IACT_MIN_BLOCKS_RENDER_HEX
+#define IACT_MIN_BLOCKS_RENDER_HEX 5 // render on a hard hex camera without level-3 culling: five resident blocks at 51 registers
+#endif                               // (a few dozen bytes of spills) beat four at 62 by 2 %; the other instantiations lose 0-6 %
 #ifndef IACT_MIN_BLOCKS_STAGES
 #define IACT_MIN_BLOCKS_STAGES 3
 #endif
@@ -442,7 +445,8 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
 // early).  Response matrix: one block owns a source row (its histogram is the row), so whole block items are
 // pulled from the same counter (queue.counter == nullptr there selects a static grid-stride split).
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
-__global__ void __launch_bounds__(256, STAGES ? IACT_MIN_BLOCKS_STAGES : IACT_MIN_BLOCKS)
+__global__ void __launch_bounds__(256, STAGES ? IACT_MIN_BLOCKS_STAGES
+                                              : ((MODE == MODE_RENDER && SENS == SENS_HEX && !SUB) ? IACT_MIN_BLOCKS_RENDER_HEX : IACT_MIN_BLOCKS))
 trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
              const LaunchPlan plan, const QueuePlan queue, const FacetLists fl, float* __restrict__ out,
              float* __restrict__ out_val, int* __restrict__ out_pix) {
