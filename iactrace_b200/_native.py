@@ -96,6 +96,8 @@ _SIGNATURES = {
     "iact_accumulate": (C.c_int, [C.POINTER(IactSensor), _fp, _fp, _fp, C.c_longlong, _fp, _fp]),
     "iact_cull_stats": (C.c_int, [C.POINTER(IactScene), _fp, C.c_int, C.c_int, _fp, _fp]),
     "iact_probe_fp32": (C.c_int, [C.c_int, C.POINTER(C.c_double), _fp]),
+    "iact_work_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_longlong, C.POINTER(C.c_int),
+                                 C.POINTER(C.c_longlong)]),
     "iact_probe_smem_atomics": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double), _fp]),
 }
 

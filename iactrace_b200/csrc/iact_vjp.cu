@@ -618,3 +618,23 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     iact_count_launch();
     return iact_check_cuda(cudaGetLastError(), "vjp_finalize_kernel launch");
 }
+
+extern "C" int iact_work_plan(int kind, int n_facets, int n_samples, int n_sources, int has_obstructions, long long resident_warps,
+                              int* out6, long long* n_units) {
+    IACT_REQUIRE(out6 && n_units, "null output");
+    IACT_REQUIRE(n_facets > 0 && n_samples > 0 && n_sources > 0 && resident_warps > 0, "sizes must be positive");
+    IACT_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (render) or 1 (vjp)");
+    SceneDev d;
+    memset(&d, 0, sizeof(d));
+    d.F = n_facets; d.M = n_samples; d.cull = has_obstructions != 0;
+    if (kind == 0) {
+        const QueuePlan q = make_queue_plan(d, n_sources, resident_warps);
+        out6[0] = q.facets_per_unit; out6[1] = q.runs; out6[2] = q.msplit; out6[3] = q.msize; out6[4] = out6[5] = 0;
+        *n_units = q.n_units;
+    } else {
+        const VjpPlan p = make_vjp_plan(d, n_sources, resident_warps);
+        out6[0] = p.slen; out6[1] = p.sruns; out6[2] = p.msplit; out6[3] = p.msize; out6[4] = out6[5] = 0;
+        *n_units = p.n_units;
+    }
+    return IACT_OK;
+}

@@ -215,6 +215,16 @@ int iact_cull_stats(const IactScene* scene, const float* sources, int n_sources,
 int iact_probe_fp32(int iters, double* out_flops, void* stream);
 int iact_probe_smem_atomics(int iters, int n_distinct, double* out_atomics, void* stream);
 
+/* Work decomposition of the trace / VJP kernels, host arithmetic only (no device needed): how n_facets x n_samples
+ * x n_sources rays are cut into the units the warps pull from the work queue.
+ * kind 0 = render / render_debug: out6 = {facets per unit, facet runs, sample parts, rows per part, 0, 0};
+ *                                 unit u -> source u / (runs * parts), run (u / parts) % runs, part u % parts.
+ * kind 1 = render_vjp:            out6 = {sources per unit, source runs, sample parts, rows per part, 0, 0};
+ *                                 unit u -> source run u % sruns, part (u / sruns) % parts, facet u / (sruns * parts).
+ * *n_units receives the unit count.  Used by the CPU tests to check that every ray is covered exactly once. */
+int iact_work_plan(int kind, int n_facets, int n_samples, int n_sources, int has_obstructions, long long resident_warps,
+                   int* out6, long long* n_units);
+
 /* Number of kernel launches issued by this library in this process (bench "gpu_launches"). */
 long long iact_launch_count(void);
 
