@@ -2,18 +2,22 @@
 // (reference core/render.py:174-324, _trace_single_mirror :118-157) with exact obstruction culling.
 //
 // Work decomposition:
-//   block item  = (source s, chunk of facets)      -> grid-stride over items
-//   warp item   = (facet f, sample range)          -> warps of the block stride over the chunk
-//   lane        = one ray (sample m of facet f seen from source s)
+//   warp item   = (facet f, source s, sample range)          lane = one ray (sample m of facet f seen from source s)
+//   render / render_debug: persistent grid; every warp pulls units (source, run of <= 8 facets, sample part) from a
+//                          global counter (QueuePlan) -- no warp idles while another still has a backlog
+//   response matrix:       one block owns a source row (its shared histogram is the row); whole rows are pulled
+//                          from the same counter, the warps of the block stride over the row's facets
 // Culling is hierarchical and conservative (a primitive is dropped only if no ray of a beam can
 // touch it, with margins far above float32 rounding):
 //   level 1 (facet_cull_kernel, once per call): facet x all sources -> per-facet candidate list in HBM/L2
 //   level 2 (per warp item): (facet, source) beam against the facet list -> per-warp list in shared memory
+//   level 3 (binned tables, SUB = true): every run of 32 table rows against the warp's list -> per-iteration mask
+//            (strip test for far / parallel sources, capsule test otherwise)
 // Lanes then test their ray only against the warp's short list (warp-uniform loop).
-// Hex cameras are binned into a block-private shared-memory histogram with warp-aggregated adds
-// (one shared atomic per distinct pixel per warp), flushed once per source (response matrix: plain
-// coalesced stores) or once per block (render: one red.global per touched pixel); square cameras
-// use red.global directly.
+// Hex cameras are binned into a block-private shared-memory histogram through a per-warp register cache of up to
+// three pixels (PixCache, with a fast path that skips rounding and lookup when every lane stays in the cached
+// hexagon), flushed once per source (response matrix: plain coalesced stores) or once per block (render: one
+// red.global per touched pixel); square cameras use red.global directly.
 #include "iact_cull.cuh"
 
 namespace {
