@@ -23,6 +23,25 @@ def _leaves(tel, sensor_idx):
     return out
 
 
+def with_leaves(tel, sensor_idx, new):
+    """Functional copy of ``tel`` whose differentiable leaves (in ``_leaves`` order) are replaced by ``new``."""
+    from .render import _get_stages
+    from .._util import replace
+    it = iter(new)
+    swap = {}
+    stages = _get_stages(tel.mirror_groups)
+    for g in stages.get(0, []):
+        swap[id(g)] = replace(g, positions=next(it), rotations=next(it), perturbation_scale=next(it), weights=next(it))
+    s = tel.sensors[sensor_idx]
+    sensors = list(tel.sensors)
+    sensors[sensor_idx] = replace(s, position=next(it), rotation=next(it))
+    for k in stages:
+        if k != 0:
+            for g in stages[k]:
+                swap[id(g)] = replace(g, positions=next(it), rotations=next(it))
+    return replace(tel, mirror_groups=[swap.get(id(g), g) for g in tel.mirror_groups], sensors=sensors)
+
+
 def needs_grad(tel, sources, values, sensor_idx) -> bool:
     if not torch.is_grad_enabled():
         return False
@@ -35,7 +54,9 @@ class _Render(torch.autograd.Function):
     def forward(ctx, tel, source_type, sensor_idx, src, val, *leaves):
         from .render import build_scene, _stype
         ctx.tel, ctx.source_type, ctx.sensor_idx = tel, source_type, sensor_idx
-        ctx.save_for_backward(src, val)
+        # the leaves are saved too: autograd then refuses a backward after one of them was edited in place
+        # (the backward pass rebuilds the scene from the telescope's current tensors)
+        ctx.save_for_backward(src, val, *leaves)
         with torch.no_grad():
             keep = []
             sc, sensor = build_scene(tel, sensor_idx, keep)
@@ -50,7 +71,7 @@ class _Render(torch.autograd.Function):
     def backward(ctx, g_img):
         from .render import build_scene, _stype, _get_stages
         tel, sensor_idx = ctx.tel, ctx.sensor_idx
-        src, val = ctx.saved_tensors
+        src, val = ctx.saved_tensors[:2]
         stages = _get_stages(tel.mirror_groups)
         g_img = contig(g_img.to(torch.float32))
         dev = src.device
@@ -99,8 +120,8 @@ class _Render(torch.autograd.Function):
 
 
 def render_with_grad(tel, sources, values, source_type, sensor_idx):
-    N.require_cuda()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    from .render import scene_device
+    dev = scene_device(tel)
     src = f32(sources, dev).reshape(-1, 3).contiguous()
     val = f32(values, dev).reshape(-1).contiguous()
     return _Render.apply(tel, source_type, sensor_idx, src, val, *_leaves(tel, sensor_idx))

@@ -70,6 +70,13 @@ def _world_tables(tel, stage0, later_stages=False):
     return world, bounds, chunks
 
 
+def _stage_sig(groups):
+    ts = []
+    for g in groups:
+        ts += [g.positions, g.rotations, g.offsets, g.radii if g.kind == "disk" else g.vertices]
+    return (_tensor_sig(ts), tuple((g.curvature, g.conic, tuple(float(a) for a in g.aspheric)) for g in groups))
+
+
 def _stage_tables(tel, groups, dev):
     """Flat (n, IACT_MIRROR_REC) record table for one optical stage >= 1."""
     recs, verts = [], []
@@ -100,11 +107,13 @@ def _stage_tables(tel, groups, dev):
 def _obstruction_tables(tel):
     """Per-type dense obstruction tables.  Several groups of one type are concatenated: the shadow
     mask is a product over groups of min-over-primitives (``render.py:37-41``), i.e. an any-hit."""
-    hit = tel._cache.get("obs")
-    if hit is not None:
-        return hit
     from .obstructions import CylinderGroup, BoxGroup, SphereGroup, OrientedBoxGroup, TriangleGroup
     groups = tel.obstruction_groups or []
+    # keyed on (storage, version) of every obstruction tensor: an in-place edit or a swapped group rebuilds the tables
+    sig = tuple((type(g).__name__, _tensor_sig([v for v in vars(g).values() if isinstance(v, torch.Tensor)])) for g in groups)
+    hit = tel._cache.get("obs")
+    if hit is not None and hit[0] == sig:
+        return hit[1]
 
     def cat(cls, names):
         gs = [g for g in groups if isinstance(g, cls)]
@@ -119,7 +128,7 @@ def _obstruction_tables(tel):
                 sph=cat(SphereGroup, ("centers", "radii")),
                 obox=cat(OrientedBoxGroup, ("centers", "half_extents", "rotations")),
                 tri=cat(TriangleGroup, ("v0", "v1", "v2")))
-    tel._cache["obs"] = tabs
+    tel._cache["obs"] = (sig, tabs)
     return tabs
 
 
@@ -152,10 +161,14 @@ def build_scene(tel, sensor_idx: int, keep: list, cull: bool | None = None):
         raise ValueError(f"at most {N.MAX_STAGES} optical stages beyond the primary are supported")
     sc.n_stages = len(later)
     for i, k in enumerate(later):
-        ck = ("stage", k)
-        if ck not in tel._cache:
-            tel._cache[ck] = _stage_tables(tel, stages[k], dev)
-        rec, verts = tel._cache[ck]
+        # keyed like the world table: the alignment-fit loop (render -> backward -> optimizer.step()) edits the
+        # stage >= 1 poses in place, and the next render must see them
+        ck, sig = ("stage", k), _stage_sig(stages[k])
+        hit = tel._cache.get(ck)
+        if hit is None or hit[0] != sig:
+            hit = (sig,) + _stage_tables(tel, stages[k], dev)
+            tel._cache[ck] = hit
+        rec, verts = hit[1], hit[2]
         keep += [rec, verts]
         sc.stages[i].n_mirrors = rec.shape[0]
         sc.stages[i].records = N.ptr(rec)
@@ -165,9 +178,38 @@ def build_scene(tel, sensor_idx: int, keep: list, cull: bool | None = None):
     return sc, sensor
 
 
-def _inputs(sources, values):
+def scene_device(tel) -> torch.device:
+    """The CUDA device the telescope's tensors live on (the kernels dereference them, so inputs, outputs and the
+    launch must be there too); the current device for an empty telescope."""
     N.require_cuda()
-    dev = torch.device("cuda", torch.cuda.current_device())
+    devs = {g.positions.device for g in tel.mirror_groups}
+    devs |= {v.device for g in (tel.obstruction_groups or []) for v in vars(g).values() if isinstance(v, torch.Tensor)}
+    devs |= {s.position.device for s in tel.sensors if isinstance(getattr(s, "position", None), torch.Tensor)}
+    if len(devs) > 1:
+        raise ValueError(f"telescope tensors live on several devices: {sorted(map(str, devs))}")
+    dev = devs.pop() if devs else torch.device("cuda", torch.cuda.current_device())
+    if dev.type != "cuda":
+        raise RuntimeError("iactrace_b200: the telescope was built without a CUDA device; the ray-tracing path has no CPU fallback")
+    return dev
+
+
+def _on_scene_device(fn):
+    """Run a render entry point with the telescope's device current (kernel launches, allocations and the stream
+    all follow the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(tel, *a, **k):
+        dev = scene_device(tel)
+        if dev.index == torch.cuda.current_device():
+            return fn(tel, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(tel, *a, **k)
+    return wrapped
+
+
+def _inputs(tel, sources, values):
+    dev = scene_device(tel)
     src = contig(f32(sources, dev).detach().reshape(-1, 3))
     val = contig(f32(values, dev).detach().reshape(-1))
     if src.shape[0] != val.shape[0]:
@@ -186,12 +228,13 @@ def _stype(source_type) -> int:
     return N.SOURCE_POINT if source_type == "point" else N.SOURCE_PARALLEL
 
 
+@_on_scene_device
 def render(tel, sources, values, source_type="point", sensor_idx: int = 0) -> torch.Tensor:
     """Render sources through the telescope onto a sensor -> image of the sensor's shape."""
     from .autograd import needs_grad, render_with_grad
     if needs_grad(tel, sources, values, sensor_idx):
         return render_with_grad(tel, sources, values, source_type, sensor_idx)
-    src, val, dev = _inputs(sources, values)
+    src, val, dev = _inputs(tel, sources, values)
     keep = []
     sc, sensor = build_scene(tel, sensor_idx, keep)
     out = torch.empty(sensor.get_accumulator_shape(), dtype=torch.float32, device=dev)
@@ -202,11 +245,12 @@ def render(tel, sources, values, source_type="point", sensor_idx: int = 0) -> to
     return _out(out)
 
 
+@_on_scene_device
 def render_debug(tel, sources, values, source_type="point", sensor_idx: int = 0, return_pixels: bool = False):
     """Raw hits without accumulation -> (points (F*S*M,2), values (F*S*M,)), facet-major then source
     then sample (``render.py:223-268``).  ``return_pixels`` adds the int32 pixel id each ray is
     assigned by the (hard) sensor, -1 = rejected."""
-    src, val, dev = _inputs(sources, values)
+    src, val, dev = _inputs(tel, sources, values)
     keep = []
     sc, _ = build_scene(tel, sensor_idx, keep)
     if sc is None:
@@ -221,9 +265,10 @@ def render_debug(tel, sources, values, source_type="point", sensor_idx: int = 0,
     return _out((xy, v, pix) if return_pixels else (xy, v))
 
 
+@_on_scene_device
 def render_response_matrix(tel, sources, values, source_type="point", sensor_idx: int = 0) -> torch.Tensor:
     """Source-to-pixel response matrix (S, n_pixels): row i is the flattened image of source i alone."""
-    src, val, dev = _inputs(sources, values)
+    src, val, dev = _inputs(tel, sources, values)
     keep = []
     sc, sensor = build_scene(tel, sensor_idx, keep)
     npix = math.prod(sensor.get_accumulator_shape())

@@ -50,8 +50,20 @@ __device__ __forceinline__ void splat_soft_hex(const SensDev& se, const LUT* lut
     }
 }
 
+// Square cameras have 1.5-2.1 Mpixel, far too many for a block-private histogram, so rays add straight into global
+// memory.  A single image (render, iact_accumulate) is accumulated in FLOAT64 (red.global.add.f64 into a scratch
+// image, converted to float32 by square_convert_kernel): a bright pixel receives 1e4-1e5 addends in a launch-dependent
+// order, which in float32 wanders by a few 1e-4 from run to run (hazard H6); in float64 the order-dependent part is
+// ~1e-12, so the float32 image is the correctly rounded sum and reproducible.  The reference sums per facet with
+// segment_sum and adds the facet images (square.py:87, render.py:216).  Response-matrix rows (few addends per pixel,
+// S x W x H outputs) stay float32.
+#ifndef IACT_SQUARE_F64
+#define IACT_SQUARE_F64 1
+#endif
+
 // DifferentiableSquareSensor.accumulate (square.py:144-172)
-__device__ __forceinline__ void splat_soft_square(const SensDev& se, float x, float y, float val, float* img) {
+template <typename ACC>
+__device__ __forceinline__ void splat_soft_square(const SensDev& se, float x, float y, float val, ACC* img) {
     const float xp = (x - se.x0) * se.inv_dx, yp = (y - se.y0) * se.inv_dy;
     const float xb = floorf(xp), yb = floorf(yp);
     const int K = se.ksize;
@@ -66,7 +78,7 @@ __device__ __forceinline__ void splat_soft_square(const SensDev& se, float x, fl
                 const float w = gauss_half((dx * dx + dy * dy) * inv_s2);
                 if (pass == 0) { wsum += w; continue; }
                 const int xi = (int)xb + ox, yi = (int)yb + oy;
-                if (xi >= 0 && xi < se.W && yi >= 0 && yi < se.H) atomicAdd(img + (size_t)yi * se.W + xi, val * (w / wsum));
+                if (xi >= 0 && xi < se.W && yi >= 0 && yi < se.H) atomicAdd(img + (size_t)yi * se.W + xi, (ACC)(val * (w / wsum)));
             }
 }
 
@@ -375,8 +387,14 @@ __device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx
                 cache.add(cx.hist, add ? pix : -1, val, pcx, pcy);
             }
         } else if (add) {
-            if (cx.soft) splat_soft_square(sc.sens, x, y, val, gout);
-            else { const int pix = square_pixel(sc.sens, x, y); if (pix >= 0) atomicAdd(gout + pix, val); }
+            if (MODE == MODE_RENDER && IACT_SQUARE_F64) {            // gout is the float64 scratch image (run())
+                double* g64 = reinterpret_cast<double*>(gout);
+                if (cx.soft) splat_soft_square(sc.sens, x, y, val, g64);
+                else { const int pix = square_pixel(sc.sens, x, y); if (pix >= 0) atomicAdd(g64 + pix, (double)val); }
+            } else {
+                if (cx.soft) splat_soft_square(sc.sens, x, y, val, gout);
+                else { const int pix = square_pixel(sc.sens, x, y); if (pix >= 0) atomicAdd(gout + pix, val); }
+            }
         }
     }
 }
@@ -588,16 +606,33 @@ __global__ void __launch_bounds__(256) cull_stats_kernel(const __grid_constant__
     if (lane == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); atomicAdd(out + 2, c); atomicAdd(out + 3, l1); }
 }
 
-// sensor.accumulate on free-standing hits: one thread per hit, red.global into the image.
+// float64 scratch image -> float32 image (square cameras, see IACT_SQUARE_F64)
+__global__ void __launch_bounds__(256) square_convert_kernel(const double* __restrict__ acc, float* __restrict__ out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (float)acc[i];
+}
+int launch_square_convert(const double* acc, float* out, size_t n, cudaStream_t st) {
+    const unsigned grid = (unsigned)std::min<size_t>((n + 255) / 256, (size_t)sm_count() * 8);
+    square_convert_kernel<<<grid, 256, 0, st>>>(acc, out, n);
+    iact_count_launch();
+    return iact_check_cuda(cudaGetLastError(), "square_convert_kernel launch");
+}
+
+// sensor.accumulate on free-standing hits: one thread per hit, red.global into the image (`out64` = float64 scratch
+// image of the square cameras when IACT_SQUARE_F64).
 __global__ void __launch_bounds__(256) accumulate_kernel(const SensDev se, const float* __restrict__ x, const float* __restrict__ y,
-                                                         const float* __restrict__ v, long long n, float* __restrict__ out) {
+                                                         const float* __restrict__ v, long long n, float* __restrict__ out,
+                                                         double* __restrict__ out64) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float val = v[i];
     switch (se.kind) {
-        case IACT_SENSOR_SQUARE: { const int p = square_pixel(se, x[i], y[i]); if (p >= 0) atomicAdd(out + p, val); break; }
+        case IACT_SENSOR_SQUARE: {
+            const int p = square_pixel(se, x[i], y[i]);
+            if (p >= 0) { if (out64) atomicAdd(out64 + p, (double)val); else atomicAdd(out + p, val); }
+            break;
+        }
         case IACT_SENSOR_HEX:    { const int p = hex_pixel(se, se.lookup, x[i], y[i]); if (p >= 0) atomicAdd(out + p, val); break; }
-        case IACT_SENSOR_SOFT_SQUARE: splat_soft_square(se, x[i], y[i], val, out); break;
+        case IACT_SENSOR_SOFT_SQUARE: if (out64) splat_soft_square(se, x[i], y[i], val, out64); else splat_soft_square(se, x[i], y[i], val, out); break;
         default: splat_soft_hex(se, se.lookup, x[i], y[i], val, out); break;
     }
 }
@@ -671,7 +706,14 @@ int run(const IactScene* scene, const float* sources, const float* values, int S
     const bool empty = S == 0 || d.F == 0 || d.M == 0;
     if (!empty) IACT_REQUIRE(sources && values, "null sources/values");
     LaunchPlan plan = make_plan(d, std::max(S, 1), mode);
-    if (mode == MODE_RENDER) {
+    Scratch acc64;                                                           // float64 image of a square camera
+    float* final_out = out;
+    if (mode == MODE_RENDER && !hex && IACT_SQUARE_F64 && !empty) {
+        rc = acc64.alloc(npix * sizeof(double), st);
+        if (rc) return rc;
+        IACT_CUDA(cudaMemsetAsync(acc64.ptr, 0, npix * sizeof(double), st));
+        out = reinterpret_cast<float*>(acc64.ptr);
+    } else if (mode == MODE_RENDER) {
         IACT_CUDA(cudaMemsetAsync(out, 0, npix * sizeof(float), st));        // render.py:198-199,218
     } else if (mode == MODE_MATRIX) {
         if (empty || !(hex && plan.n_chunks == 1)) IACT_CUDA(cudaMemsetAsync(out, 0, (size_t)S * npix * sizeof(float), st));
@@ -687,7 +729,10 @@ int run(const IactScene* scene, const float* sources, const float* values, int S
     // level-1 lists pay off once a facet is seen from several sources
     if (d.cull && S >= 4) { rc = run_facet_cull(d, sources, S, source_type, scr, fl, st); if (rc) return rc; }
     switch (mode) {
-        case MODE_RENDER: return launch_src<MODE_RENDER>(source_type, d, sources, values, plan, fl, out, out_val, out_pix, st);
+        case MODE_RENDER:
+            rc = launch_src<MODE_RENDER>(source_type, d, sources, values, plan, fl, out, out_val, out_pix, st);
+            if (rc || !acc64.ptr) return rc;
+            return launch_square_convert(reinterpret_cast<const double*>(acc64.ptr), final_out, npix, st);
         case MODE_MATRIX: return launch_src<MODE_MATRIX>(source_type, d, sources, values, plan, fl, out, out_val, out_pix, st);
         default:          return launch_src<MODE_DEBUG>(source_type, d, sources, values, plan, fl, out, out_val, out_pix, st);
     }
@@ -736,11 +781,20 @@ extern "C" int iact_accumulate(const IactSensor* sensor, const float* x, const f
     const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
     const size_t npix = hex ? (size_t)d.sens.npix : (size_t)d.sens.W * d.sens.H;
     cudaStream_t st = (cudaStream_t)stream;
-    IACT_CUDA(cudaMemsetAsync(out, 0, npix * sizeof(float), st));
+    Scratch acc64;
+    if (!hex && IACT_SQUARE_F64 && n > 0) {
+        rc = acc64.alloc(npix * sizeof(double), st);
+        if (rc) return rc;
+        IACT_CUDA(cudaMemsetAsync(acc64.ptr, 0, npix * sizeof(double), st));
+    } else {
+        IACT_CUDA(cudaMemsetAsync(out, 0, npix * sizeof(float), st));
+    }
     if (n == 0) return IACT_OK;
-    accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.sens, x, y, values, n, out);
+    accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.sens, x, y, values, n, out, reinterpret_cast<double*>(acc64.ptr));
     iact_count_launch();
-    return iact_check_cuda(cudaGetLastError(), "accumulate_kernel launch");
+    rc = iact_check_cuda(cudaGetLastError(), "accumulate_kernel launch");
+    if (rc || !acc64.ptr) return rc;
+    return launch_square_convert(reinterpret_cast<const double*>(acc64.ptr), out, npix, st);
 }
 
 extern "C" int iact_render(const IactScene* scene, const float* sources, const float* values, int n_sources,

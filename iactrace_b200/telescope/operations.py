@@ -69,9 +69,9 @@ def apply_misalignment_to_group(telescope, group_idx: int, sigma_h: float, sigma
     k1, k2 = R.split(key)
     dh = R.normal(k1, n) * (sigma_h / 3600.0)
     dv = R.normal(k2, n) * (sigma_v / 3600.0)
-    rot = g.rotations.detach().clone()
-    rot[:, 0] += dh.to(rot.device)
-    rot[:, 1] += dv.to(rot.device)
+    # out of place, like the reference's `.at[:, 0].add(...)`: the edit stays differentiable w.r.t. the original rotations
+    dev = g.rotations.device
+    rot = g.rotations + torch.stack([dh.to(dev), dv.to(dev), torch.zeros(n, dtype=torch.float32, device=dev)], dim=1)
     return _with_group(telescope, group_idx, replace(g, rotations=rot))
 
 
@@ -79,8 +79,9 @@ def apply_displacement_to_group(telescope, group_idx: int, sigma_z: float, key):
     """Gaussian z displacement of mirror positions (``operations.py:201-229``)."""
     g = telescope.mirror_groups[group_idx]
     dz = R.normal(key, len(g)) * sigma_z
-    pos = g.positions.detach().clone()
-    pos[:, 2] += dz.to(pos.device)
+    dev = g.positions.device
+    zero = torch.zeros(len(g), dtype=torch.float32, device=dev)
+    pos = g.positions + torch.stack([zero, zero, dz.to(dev)], dim=1)       # out of place: differentiable (see above)
     return _with_group(telescope, group_idx, replace(g, positions=pos))
 
 
@@ -128,9 +129,10 @@ def set_sensor_rotation(telescope, idx: int, rotation):
 
 def focus(telescope, delta_z: float, sensor_idx: int = 0):
     """Move a sensor along z (``operations.py:355-371``)."""
-    pos = telescope.sensors[sensor_idx].position.detach().clone()
-    pos[2] += delta_z
-    return set_sensor_position(telescope, sensor_idx, pos)
+    old = telescope.sensors[sensor_idx].position
+    dz = delta_z if isinstance(delta_z, torch.Tensor) else torch.tensor(float(delta_z), dtype=torch.float32)
+    e_z = torch.tensor([0.0, 0.0, 1.0], dtype=torch.float32, device=old.device)
+    return set_sensor_position(telescope, sensor_idx, old + dz.to(old.device) * e_z)   # differentiable in delta_z and position
 
 
 def get_sensor_count(telescope) -> int:

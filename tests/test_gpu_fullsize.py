@@ -44,6 +44,28 @@ def test_config2_ct5_4096_sources_properties(ct5, sensor_idx):
     assert 0.5 * 614 < float(clear.sum()) / float(val.sum()) < 614
 
 
+@pytest.mark.parametrize("name,sensor_idx,M,n_src", [("CT5", 2, 115, 512), ("CT3", 1, 1000, 64)])
+def test_lid_images_equal_float64_binning_of_own_rays(name, sensor_idx, M, n_src, ct5):
+    """CT5 lid (1431 x 1501) and CT3 lid (1024 x 1536): the rendered image against the float64 binning of the kernel's
+    own per-ray output (render_debug pixel ids + values) on ALL pixels, at 1e-4 relative, and run-to-run."""
+    tel = ct5 if name == "CT5" else build_telescope(load_packed_config("CT3"), I.MCIntegrator(M), I.random.key(0))
+    src = torch.from_numpy(point_grid(64, 1.5 if name == "CT5" else 1.0)[:: 4096 // n_src]).cuda()
+    val = torch.linspace(0.5, 1.5, len(src), device="cuda")
+    from iactrace_b200.core import render_debug
+    img = render(tel, src, val, "point", sensor_idx)
+    _, v, pix = render_debug(tel, src, val, "point", sensor_idx, return_pixels=True)
+    ok = pix >= 0
+    own = torch.zeros(img.numel(), dtype=torch.float64, device="cuda").index_add_(0, pix[ok].long(), v[ok].double())
+    lit = own > 0
+    assert int(lit.sum()) > 1000
+    err = ((img.reshape(-1).double() - own).abs() / own.clamp_min(1e-30))[lit].max()
+    assert float(err) <= 1e-6, float(err)                    # the bar is 1e-4; float64 accumulation leaves one float32 rounding
+    assert float(img.reshape(-1)[~lit].abs().max()) == 0.0
+    again = render(tel, src, val, "point", sensor_idx)
+    rel = ((again - img).abs() / img.clamp_min(1e-30))[img > 0].max()
+    assert float(rel) <= 2e-5, float(rel)
+
+
 def test_config4_ct3_response_matrix_properties():
     """Config 4: CT3 + roughness 24", 64x64 parallel directions over 5.5 deg, M = 64 -> (4096, 960)."""
     tel = build_telescope(load_packed_config("CT3"), I.MCIntegrator(64), I.random.key(42)).apply_roughness(24)
@@ -74,9 +96,13 @@ def test_config3_cassegrain_1e9_rays_properties():
     src, val = torch.from_numpy(d).cuda(), torch.from_numpy(flux).cuda()
     full = render(tel, src, val, "parallel", 0)
     assert full.shape == (1024, 1024) and torch.isfinite(full).all() and float(full.min()) >= 0.0
-    # a star puts its 1e5 rays into a dozen pixels by per-ray float32 atomics in launch-dependent order: the sum of
-    # 1e4-1e5 addends carries a few 1e-4 of relative rounding noise (the reference's float32 segment_sum does too)
-    tol = dict(rtol=1e-3, atol=5e-6 * float(full.max()))
+    # a star puts its 1e5 rays into a dozen pixels; the square-camera image is accumulated in float64 and rounded
+    # once (iact_render.cu, IACT_SQUARE_F64), so the stated per-pixel bar (1e-4 relative, BASELINE.json) holds with
+    # room to spare and two launches agree to float32 rounding of the final conversion
+    tol = dict(rtol=1e-4, atol=1e-6 * float(full.max()))
+    again = render(tel, src, val, "parallel", 0)
+    rel = ((again - full).abs() / full.clamp_min(1e-6 * float(full.max()))).max()
+    assert float(rel) <= 2e-5, float(rel)
     # additivity over a partition of the directions, linearity in the fluxes
     a = render(tel, src[:3000], val[:3000], "parallel", 0)
     b = render(tel, src[3000:], val[3000:], "parallel", 0)

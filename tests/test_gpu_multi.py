@@ -1,5 +1,6 @@
-"""Two real GPUs over NCCL: the source-sharded render + all-reduce equals the single-GPU render, and
-the row-sharded response matrix tiles the full matrix.  Skipped with fewer than two devices."""
+"""Two real GPUs over NCCL: the source-sharded render + all-reduce equals the single-GPU render, the
+row-sharded response matrix tiles the full matrix, and the sharded gradient (per-rank VJP + one all-reduce of
+the packed leaf gradients) equals the single-GPU gradient.  Skipped with fewer than two devices."""
 import os
 import socket
 
@@ -28,9 +29,18 @@ def _worker(rank, world, port, q):
         img = render_sharded(tel, src, val, "point", 0)
         full, _ = response_matrix_sharded(tel, src, val, "point", 0, gather=True)
         rows, (a, b) = response_matrix_sharded(tel, src, val, "point", 0)
+        # sharded gradient: every rank ends up with the full gradient of a replicated loss
+        g = tel.mirror_groups[0]
+        g.rotations.requires_grad_(True)
+        g.perturbation_scale.requires_grad_(True)
+        vg = val.clone().requires_grad_(True)
+        G = torch.linspace(-1.0, 1.0, 960, device="cuda")
+        gi = render_sharded(tel, src, vg, "point", 0)
+        (gi * G).sum().backward()
         torch.cuda.synchronize()
         q.put((rank, img.cpu().numpy(), full.cpu().numpy(), rows.cpu().numpy(), a, b,
-               tel.mirror_groups[0].points[:2, :3].cpu().numpy()))
+               tel.mirror_groups[0].points[:2, :3].cpu().numpy(), gi.detach().cpu().numpy(),
+               g.rotations.grad.cpu().numpy(), g.perturbation_scale.grad.cpu().numpy(), vg.grad.cpu().numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -61,9 +71,19 @@ def test_two_gpu_sharded_render_matches_single_gpu():
     val = torch.linspace(0.5, 1.5, len(src), device="cuda")
     want = render(tel, src, val, "point", 0).cpu().numpy()
     want_m = render_response_matrix(tel, src, val, "point", 0).cpu().numpy()
+    g = tel.mirror_groups[0]
+    g.rotations.requires_grad_(True)
+    g.perturbation_scale.requires_grad_(True)
+    vg = val.clone().requires_grad_(True)
+    (render(tel, src, vg, "point", 0) * torch.linspace(-1.0, 1.0, 960, device="cuda")).sum().backward()
+    want_g = [t.grad.cpu().numpy() for t in (g.rotations, g.perturbation_scale, vg)]
+    assert np.abs(want_g[0]).max() > 0 and np.abs(want_g[2]).max() > 0
     assert np.array_equal(res[0][6], res[1][6])                   # identical samples on both ranks
-    for rank, img, full, rows, a, b, _ in res:
+    for rank, img, full, rows, a, b, _, gimg, g_rot, g_scale, g_val in res:
         np.testing.assert_allclose(img, want, rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(gimg, want, rtol=2e-5, atol=1e-7)
         np.testing.assert_allclose(full, want_m, rtol=2e-6, atol=1e-9)
         np.testing.assert_allclose(rows, want_m[a:b], rtol=2e-6, atol=1e-9)
+        for got, w in zip((g_rot, g_scale, g_val), want_g):
+            np.testing.assert_allclose(got, w, rtol=1e-4, atol=2e-5 * np.abs(w).max())
     assert (res[0][4], res[0][5], res[1][4], res[1][5]) == (0, 25, 25, 49)

@@ -161,3 +161,67 @@ def test_two_stage_gradients_through_the_secondary(polygon_secondary):
     np.testing.assert_allclose(img, oimg, rtol=5e-3, atol=2e-4 * oimg.max())
     _check(got, want, ["rotations", "positions", "scale", "weights", "values", "sources", "sensor_position",
                        "sensor_rotation", "stage0_positions", "stage0_rotations"], 1e-2)
+
+
+def test_in_place_optimizer_steps_reach_the_kernels():
+    """The alignment-fit loop: render -> backward -> optimizer.step() edits the leaves IN PLACE.  The stage >= 1
+    record table, the obstruction tables and the world table are cached on the Telescope keyed on (storage, version),
+    so the second render must see the moved secondary and the gradient must match the oracle at the NEW pose."""
+    from golden.cases import cfg_cassegrain
+    tel = build_telescope(cfg_cassegrain(), I.MCIntegrator(16), I.random.key(0)).apply_roughness(20)
+    sq = tel.sensors[0]
+    tel = tel.replace_sensor(DifferentiableSquareSensor(sq.position, sq.rotation, 32, 32, (-0.5, 0.5, -0.5, 0.5),
+                                                        sigma=0.8, kernel_size=2), 0)
+    d = np.array([[0.002, -0.001, -1.0], [-0.004, 0.003, -1.0], [0.0, 0.0, -1.0]])
+    src = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    val = np.array([1.0, 0.6, 1.4], np.float32)
+    G = torch.tensor(np.random.default_rng(5).normal(size=(32, 32)), device="cuda", dtype=torch.float32)
+    sec = tel.mirror_groups[1]
+    sec.positions.requires_grad_(True)
+    sec.rotations.requires_grad_(True)
+    prim = tel.mirror_groups[0]
+    prim.rotations.requires_grad_(True)
+    opt = torch.optim.SGD([sec.positions, sec.rotations, prim.rotations], lr=1.0)
+    imgs = []
+    for it in range(3):
+        opt.zero_grad()
+        img = render(tel, src, val, "parallel", 0)
+        (img * G).sum().backward()
+        imgs.append(img.detach().clone())
+        # oracle gradient at the pose this render used
+        _, want = _grads_oracle(tel, src, val, "parallel", G.cpu().numpy())
+        got = dict(stage0_positions=sec.positions.grad.cpu().numpy().astype(np.float64),
+                   stage0_rotations=sec.rotations.grad.cpu().numpy().astype(np.float64),
+                   rotations=prim.rotations.grad.cpu().numpy().astype(np.float64))
+        _check(got, want, ["stage0_positions", "stage0_rotations", "rotations"], 1e-2)
+        with torch.no_grad():                           # a visible in-place move: 2 mm of despace, 0.01 deg of tilt
+            sec.positions.grad.copy_(torch.tensor([[0.0, 0.0, -2e-3]], device="cuda"))
+            sec.rotations.grad.copy_(torch.tensor([[-1e-2, 0.0, 0.0]], device="cuda"))
+            prim.rotations.grad.mul_(0.0).add_(1e-3)
+        opt.step()
+    assert float((imgs[1] - imgs[0]).abs().max()) > 1e-3 * float(imgs[0].max())
+    assert float((imgs[2] - imgs[1]).abs().max()) > 1e-3 * float(imgs[1].max())
+    # obstruction tables follow in-place edits too
+    from iactrace_b200.core import Sphere, group_obstructions
+    t2 = I.Telescope(tel.mirror_groups, group_obstructions([Sphere([50.0, 0.0, 3.0], 0.5)]), tel.sensors)
+    with torch.no_grad():
+        a = render(t2, src, val, "parallel", 0)
+        t2.obstruction_groups[0].centers.copy_(torch.tensor([[2.0, 0.0, 3.0]], device="cuda"))   # now above a segment
+        b = render(t2, src, val, "parallel", 0)
+    assert float(b.sum()) < 0.99 * float(a.sum())
+
+
+def test_functional_edits_stay_differentiable():
+    """apply_misalignment / apply_displacement / focus are out-of-place like the reference's `.at[].add()`: a fit
+    through an edited telescope still reaches the original leaves."""
+    tel = _make("soft_hex", n_samples=8, step=150)
+    g = tel.mirror_groups[0]
+    g.rotations.requires_grad_(True)
+    g.positions.requires_grad_(True)
+    tel.sensors[0].position.requires_grad_(True)
+    t2 = ops.apply_displacement_to_group(ops.apply_misalignment_to_group(tel, 0, 15, 10, I.random.key(1)), 0, 1e-3, I.random.key(2))
+    t2 = ops.focus(t2, 0.01, 0)
+    src, val = point_grid(2, 0.8), np.ones(4, np.float32)
+    render(t2, src, val, "point", 0).square().sum().backward()
+    for t in (g.rotations, g.positions, tel.sensors[0].position):
+        assert t.grad is not None and float(t.grad.abs().max()) > 0
