@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-from .build import build, LIB
+from .build import build, build_native, LIB
 from .. import trace as otrace
 
 
@@ -24,10 +24,16 @@ class _Sensor(C.Structure):
 
 
 _lib = None
+_lib_native = None
 
 
-def _load():
-    global _lib
+def _load(variant="exact"):
+    global _lib, _lib_native
+    if variant == "native":
+        if _lib_native is None:
+            _lib_native = C.CDLL(str(build_native()))
+            _lib_native.oracle_render.restype = C.c_int
+        return _lib_native
     if _lib is None:
         build()
         _lib = C.CDLL(str(LIB))
@@ -89,9 +95,10 @@ def prepare(scene, sensor_idx=0):
     return prep
 
 
-def render(prep, sources, values, source_type="point", debug=False, threads=0):
-    """-> (image, n_threads_used) or, with debug, (xy, vals) in render_debug order."""
-    lib = _load()
+def render(prep, sources, values, source_type="point", debug=False, threads=0, variant="exact"):
+    """-> (image, n_threads_used) or, with debug, (xy, vals) in render_debug order.  ``variant="native"`` uses the
+    -O3 -march=native build (timing only; the parity tests use the bit-exact one)."""
+    lib = _load(variant)
     src = np.ascontiguousarray(sources, np.float32)
     val = np.ascontiguousarray(values, np.float32)
     F, M = prep["tp"].shape[:2]

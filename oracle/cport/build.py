@@ -20,5 +20,19 @@ def build(force: bool = False) -> Path:
     return LIB
 
 
+def build_native() -> Path:
+    """The same source at full optimisation FOR THE HOST IT RUNS ON (-march=native), FMA contraction allowed: not
+    bit-exact with the reference's op-by-op float32 any more, but the honest speed of this port on these cores
+    (bench.py reports it beside the bit-exact build).  Always rebuilt, into a temporary directory: a -march=native
+    binary must not travel between machines."""
+    import tempfile
+    out = Path(tempfile.mkdtemp(prefix="iact_oracle_native_")) / "liboracle_native.so"
+    cmd = ["gcc", "-O3", "-march=native", "-fno-math-errno", "-fopenmp", "-fPIC", "-shared", str(SRC), "-o", str(out), "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"gcc failed:\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True))

@@ -89,6 +89,41 @@ CASES = {
 }
 
 
+def cfg_ct3_full():
+    return copy.deepcopy(load_packed_config("CT3"))
+
+
+def cfg_ct5_full():
+    return copy.deepcopy(load_packed_config("CT5"))
+
+
+def cfg_pentagons():
+    """Irregular pentagon facets: the fan triangles from vertex 0 have very uneven areas (about 1 : 5 : 2), which is
+    what `jax.random.choice(p=areas)` in sample_polygon (utils/sampling.py:53) has to get right; two facet shapes in
+    one group would be split by the reference's grouping, so all facets share one vertex list."""
+    verts = [[-0.45, -0.30], [0.10, -0.42], [0.48, 0.05], [0.05, 0.40], [-0.35, 0.22]]       # counter-clockwise
+    mirrors = [dict(id=f"F{i}", template="sphere", position=[float(x), float(y), 0.02 * i], orientation=[0.3 * i, -0.2 * i, 10.0 * i],
+                    aperture=dict(type="polygon", vertices=verts), stage=0)
+               for i, (x, y) in enumerate([(-1.2, -0.6), (0.0, -0.9), (1.1, -0.4), (-0.8, 0.7), (0.5, 0.9)])]
+    return dict(telescope=dict(name="pentagons", units="m"),
+                mirror_templates=dict(sphere=dict(surface=dict(curvature=0.0333, conic=0.0, aspheric=[]))),
+                mirrors=mirrors,
+                obstructions=[dict(type="cylinder", p1=[-2.0, 0.1, 6.0], p2=[2.0, -0.1, 6.5], r=0.08)],
+                sensors=[dict(type="square", position=[0.0, 0.0, 15.0], orientation=[0.0, 0.0, 0.0], width=40, height=40,
+                              bounds=[-0.4, 0.4, -0.4, 0.4])])
+
+
+# Full-size scenes (all 380 / 876 facets, all 33 / 271 obstructions) and the uneven-polygon sampler case.  Generated
+# separately (make_golden.py --large: the reference runs on a Python-loop vmap) into reference_golden_large.npz.
+LARGE_CASES = {
+    "ct3_full": dict(cfg=cfg_ct3_full, M=8, seed=0, mode="partitionable", rough=0.0, src=_points(2, 11, 1.0), stype="point", sensors=(0,)),
+    "ct5_full": dict(cfg=cfg_ct5_full, M=4, seed=0, mode="partitionable", rough=0.0, src=_points(1, 12, 1.2), stype="point", sensors=(0,)),
+    "pentagons": dict(cfg=cfg_pentagons, M=64, seed=21, mode="partitionable", rough=0.0, src=_points(2, 13, 0.5), stype="point", sensors=(0,)),
+    "pentagons_legacy": dict(cfg=cfg_pentagons, M=33, seed=22, mode="legacy", rough=0.0, src=_points(1, 14, 0.5), stype="point", sensors=(0,)),
+}
+ALL_CASES = {**CASES, **LARGE_CASES}
+
+
 def case_values(name):
-    n = len(CASES[name]["src"])
+    n = len(ALL_CASES[name]["src"])
     return np.linspace(0.5, 1.5, n).astype(np.float32)

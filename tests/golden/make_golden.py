@@ -2,7 +2,9 @@
 
 Run in the build container only (needs /root/reference):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # the six small cases + unit vectors -> reference_golden.npz
+    python tests/golden/make_golden.py --large    # full CT3 / CT5 and the uneven-polygon sampler cases
+                                                  #   -> reference_golden_large.npz (about ten minutes)
 
 JAX/Equinox are not installable here, so the reference's unmodified Python runs on
 oracle/jaxshim (NumPy stand-in; see its README for what that does and does not pin).
@@ -29,7 +31,11 @@ from iactrace.core import (render_response_matrix, euler_to_matrix, reflect, int
 from iactrace.sensors.hexagonal import DifferentiableHexagonalSensor, _detect_hex_grid  # noqa: E402
 from iactrace.sensors.square import DifferentiableSquareSensor  # noqa: E402
 from oracle import prng  # noqa: E402
-from golden.cases import CASES, case_values  # noqa: E402
+from golden.cases import CASES, LARGE_CASES, case_values  # noqa: E402
+
+LARGE = "--large" in sys.argv
+if LARGE:
+    CASES = LARGE_CASES
 
 A = lambda x: np.asarray(x)
 out = {}
@@ -74,6 +80,12 @@ for name, c in CASES.items():
         t4 = tel.replace_sensor(soft, 0).replace_sensor(soft_sq, 1)
         out["soft/hex_image"] = A(t4(src, val, "point", sensor_idx=0))
         out["soft/square_image"] = A(t4(src, val, "point", sensor_idx=1))
+
+if LARGE:
+    np.savez_compressed(ROOT / "tests" / "golden" / "reference_golden_large.npz", **out)
+    (ROOT / "tests" / "golden" / "reference_golden_large.json").write_text(json.dumps(meta, indent=1, default=str))
+    print(f"wrote {len(out)} arrays,", (ROOT / "tests" / "golden" / "reference_golden_large.npz").stat().st_size, "bytes")
+    sys.exit(0)
 
 # unit-level vectors for every primitive (intersections.py, reflection.py, transforms.py)
 jrandom.MODE = prng.PARTITIONABLE

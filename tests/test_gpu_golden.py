@@ -14,9 +14,17 @@ from iactrace_b200 import random as R
 from iactrace_b200.core import render, render_debug, render_response_matrix
 from iactrace_b200.io import build_telescope
 from iactrace_b200.sensors import DifferentiableHexagonalSensor, DifferentiableSquareSensor
-from golden.cases import CASES, case_values
+from golden.cases import ALL_CASES as CASES, case_values
+from _bridge import sensor_to_oracle
+from _parity import ray_parity, compare_image
 
-GOLD = np.load(Path(__file__).parent / "golden" / "reference_golden.npz")
+GOLD = dict(np.load(Path(__file__).parent / "golden" / "reference_golden.npz"))
+GOLD.update(np.load(Path(__file__).parent / "golden" / "reference_golden_large.npz"))
+# Shadow / hit decisions that may differ from the executed reference: the CUDA sampler's points sit up to 3e-6 m from
+# the reference's (XLA vs CUDA sin/cos/sqrt), so a ray grazing a silhouette within that distance can flip.  Measured
+# on B200 (profiles/parity_r02.json): 0 flips in every small case, <= 2e-4 of the rays in the full-size ones.
+FLIP_BUDGET_RAYS = 1          # small cases (a few hundred rays): at most one ray
+FLIP_BUDGET_RATE = 5e-4       # full-size cases
 
 
 def _tel(name):
@@ -46,38 +54,49 @@ def test_sampler_matches_reference(name):
 
 @pytest.mark.parametrize("name", sorted(CASES))
 def test_render_matches_reference(name):
-    """Samples come from the CUDA sampler (within 3e-6 of the reference's), so hit coordinates carry
-    that through the optics: tolerance 1e-4 m on ~15-36 m lever arms, values 2e-5 relative."""
+    """Per ray, then per pixel, against the arrays the executed reference produced.  Samples come from the CUDA sampler
+    (within 3e-6 of the reference's), so hit coordinates carry that through the optics: 1e-4 m on ~15-36 m lever
+    arms, values 2e-5 relative; the reference's pixel index is the float32 binning (square.py:68-84,
+    hexagonal.py:174-191) of ITS hit points, checked against ITS image first."""
     c = CASES[name]
     tel = _tel(name)
     val = case_values(name)
     for si in c["sensors"]:
         k = f"{name}/s{si}/"
-        xy, v = render_debug(tel, c["src"], val, c["stype"], si)
-        xy, v = xy.cpu().numpy(), v.cpu().numpy()
+        xy, v, pix = render_debug(tel, c["src"], val, c["stype"], si, return_pixels=True)
+        xy, v, pix = xy.cpu().numpy(), v.cpu().numpy(), pix.cpu().numpy()
         gp, gv = GOLD[k + "debug_pts"], GOLD[k + "debug_vals"]
         assert xy.shape == gp.shape
-        flips = (v != 0) != (gv != 0)
-        assert flips.mean() <= 0.01, f"{flips.sum()} shadow/hit flips of {flips.size}"
-        both = ~flips & (gv != 0)
-        np.testing.assert_allclose(v[both], gv[both], rtol=2e-5)
-        ok = both & (np.abs(gp[:, 0]) < 1e9)
-        assert np.abs(xy[ok] - gp[ok]).max() < 1e-4
-        img = render(tel, c["src"], val, c["stype"], si).cpu().numpy()
+        so = sensor_to_oracle(tel.sensors[si])
+        budget = max(FLIP_BUDGET_RAYS / v.size, FLIP_BUDGET_RATE)
+        r = ray_parity(xy, v, pix, gp, gv, so, xy_tol=1e-4, flip_budget=budget, edge_budget=0.2, value_rtol=2e-5,
+                       index_dt=np.float32)
         gi = GOLD[k + "image"]
+        own_ref = np.bincount(r["opix"][r["opix"] >= 0], weights=gv[r["opix"] >= 0].astype(np.float64), minlength=gi.size)
+        np.testing.assert_allclose(own_ref, gi.reshape(-1), rtol=2e-5, atol=1e-7 * gi.max())     # our reading of the reference's binning
+        img = render(tel, c["src"], val, c["stype"], si).cpu().numpy()
         assert img.shape == gi.shape
+        st = compare_image(img, r, min_lit=1, min_flux_share=0.5)
+        flips = (v != 0) != (gv != 0)
         lost = np.abs(gv[flips]).sum() + np.abs(v[flips]).sum()
         assert abs(img.sum() - gi.sum()) <= 2e-4 * gi.sum() + lost
         if k + "matrix" in GOLD:
             M = render_response_matrix(tel, c["src"], val, c["stype"], si).cpu().numpy()
-            assert M.shape == GOLD[k + "matrix"].shape
-            np.testing.assert_allclose(M.sum(1), GOLD[k + "matrix"].sum(1), rtol=2e-4, atol=lost + 1e-7)
+            gM = GOLD[k + "matrix"]
+            assert M.shape == gM.shape
+            n_m = tel.mirror_groups[0].points.shape[1]
+            src_of_ray = (np.arange(v.size) // n_m) % len(c["src"])
+            for i in range(len(c["src"])):
+                compare_image(M[i], {kk: (a[src_of_ray == i] if isinstance(a, np.ndarray) else a) for kk, a in r.items()},
+                              min_lit=0, min_flux_share=0.0)
+            np.testing.assert_allclose(M.sum(1), gM.sum(1), rtol=2e-4, atol=lost + 1e-7)
         s = tel.sensors[si]
         if hasattr(s, "hex_size"):
             hg = GOLD[k + "hexgrid"]
             got = [s.hex_size, s.hex_inradius, s.grid_rotation, s.grid_offset[0], s.grid_offset[1], s.q_min, s.r_min]
             np.testing.assert_allclose(got, hg, rtol=1e-6, atol=1e-9)
             assert np.array_equal(s.lookup_table.cpu().numpy(), GOLD[k + "lookup"])
+        print(name, si, r["stats"], st)
 
 
 def test_operations_and_soft_sensors_match_reference():
@@ -98,5 +117,8 @@ def test_operations_and_soft_sensors_match_reference():
         img = render(t4, c["src"], val, "point", idx).cpu().numpy()
         g = GOLD[key]
         assert img.shape == g.shape
+        # 5e-3, not 1e-4: the hits differ from the reference's by up to 1e-4 m (sampler, above) and the Gaussian taps
+        # amplify that (d ln w = hd dhd / sigma^2); the splat arithmetic itself is checked at 1e-4 against the float64
+        # splat of the kernel's own hits in test_gpu_stages.py::test_soft_sensors_forward
         np.testing.assert_allclose(img, g, rtol=5e-3, atol=2e-4 * g.max())
         assert abs(img.sum() - g.sum()) < 1e-3 * g.sum()

@@ -134,13 +134,15 @@ def test_soft_sensors_forward():
     tel2 = tel.replace_sensor(soft, 0).replace_sensor(soft_sq, 2)
     src = np.array([[0, 0, 1e10], [1.5e8, 1e8, 1e10]], np.float32)
     val = np.array([1.0, 2.0], np.float32)
-    osc = to_oracle_scene(tel2)
+    from _parity import compare_soft_image
     for idx in (0, 2):
         img = render(tel2, src, val, "point", idx).cpu().numpy().astype(np.float64)
-        oimg = otrace.render(osc, src, val, "point", idx, np.float64)
-        assert img.shape == oimg.shape
-        # a ray within rounding noise of a hex boundary changes its 7-tap neighbourhood: allow 0.5 % on the few pixels it feeds
-        np.testing.assert_allclose(img, oimg, rtol=5e-3, atol=2e-5 * oimg.max())
+        # (1) splat arithmetic at 1e-4 against the float64 splat of the kernel's own hits; (2) end to end at 5e-3,
+        # the distance at which the float32 ORACLE sits from the float64 one as well (Gaussian taps amplify the
+        # float32 rounding of the hit coordinates; tests/_parity.py::compare_soft_image)
+        st = compare_soft_image(tel2, src, val, "point", idx)
+        print("soft sensor", idx, st)
+        assert st["max_rel_err_vs_f64_oracle"] <= max(3.0 * st["f32_oracle_vs_f64_oracle"], 1e-3)
         # splatting conserves flux that lands well inside the camera
         hard_img = render(tel, src, val, "point", idx).cpu().numpy()
         assert abs(img.sum() - hard_img.sum()) < 0.05 * hard_img.sum()

@@ -18,6 +18,7 @@ from iactrace_b200.core import render, render_debug, render_response_matrix
 from iactrace_b200.io import build_telescope, load_packed_config
 from oracle import trace as otrace
 from _bridge import to_oracle_scene, subset_config, point_grid, parallel_grid
+from _parity import compare_rays, compare_image, subset_rays
 
 EDGE_MARGIN = 1e-5   # metres
 
@@ -28,50 +29,13 @@ def _tel(name, n_samples, step=1, n_mirrors=None, seed=0):
 
 
 def _compare_rays(tel, src, val, stype, sensor_idx, xy_tol=2e-5):
-    osc = to_oracle_scene(tel)
-    xy, v, pix = render_debug(tel, src, val, stype, sensor_idx, return_pixels=True)
-    xy, v, pix = xy.cpu().numpy(), v.cpu().numpy(), pix.cpu().numpy()
-    oxy, ov = otrace.render_debug(osc, src, val, stype, sensor_idx, np.float64)
-    assert xy.shape == oxy.shape and v.shape == ov.shape
-    # shadow decisions: allow only grazing rays to differ
-    lit, olit = v != 0, ov != 0
-    flips = lit != olit
-    assert flips.mean() < 2e-4, f"{flips.sum()} shadow flips of {flips.size}"
-    both = lit & olit
-    np.testing.assert_allclose(v[both], ov[both], rtol=1e-5)
-    ok = both & (np.abs(oxy[:, 0]) < 1e9)
-    assert np.abs(xy[ok] - oxy[ok]).max() < xy_tol
-    # pixel index: bit-exact away from edges
-    s = osc["sensors"][sensor_idx]
-    oidx, ovalid, edge = otrace.pixel_index(s, oxy[:, 0], oxy[:, 1], np.float64)
-    opix = np.where(ovalid, oidx, -1)
-    if s["type"] == "hexagonal":
-        inr = s["hex_inradius"]
-        thr = 1.0 - s["edge_width"] / inr
-        near = (np.abs(edge - thr) * inr < EDGE_MARGIN) | (np.abs(edge - 1.0) * inr < EDGE_MARGIN)
-    else:
-        near = (np.abs(edge - s["edge_width"]) < EDGE_MARGIN) | (edge < EDGE_MARGIN)
-    chk = ok & ~near
-    assert np.array_equal(pix[chk], opix[chk]), f"{(pix[chk] != opix[chk]).sum()} pixel mismatches away from edges"
-    return dict(xy=xy, v=v, pix=pix, oxy=oxy, ov=ov, opix=opix, ambiguous=(ok & near) | flips, osc=osc)
+    return compare_rays(tel, src, val, stype, sensor_idx, xy_tol=xy_tol)
 
 
-def _compare_image(img, r, shape, rtol=1e-4):
-    """CUDA image vs f64 oracle accumulation; pixels touched by ambiguous rays are excluded."""
-    npx = int(np.prod(shape))
-    oimg = np.bincount(r["opix"][r["opix"] >= 0], weights=r["ov"][r["opix"] >= 0], minlength=npx)
-    tainted = np.zeros(npx, bool)
-    for arr in (r["pix"], r["opix"]):
-        a = arr[r["ambiguous"]]
-        tainted[a[a >= 0]] = True
-    got = img.reshape(-1).astype(np.float64)
-    clean = ~tainted
-    assert clean.mean() > 0.9
-    np.testing.assert_allclose(got[clean], oimg[clean], rtol=rtol, atol=1e-7 * max(oimg.max(), 1e-30))
-    # and the image must equal the binning of the kernel's own per-ray output everywhere
-    own = np.bincount(r["pix"][r["pix"] >= 0], weights=r["v"][r["pix"] >= 0].astype(np.float64), minlength=npx)
-    np.testing.assert_allclose(got, own, rtol=5e-5, atol=1e-7 * max(own.max(), 1e-30))
-    return oimg
+def _compare_image(img, r, shape, rtol=1e-4, **kw):
+    """CUDA image vs the float64 oracle (tests/_parity.py): clean pixels at 1e-4 with lit pixels provably compared,
+    the unconditional ambiguity bound on every pixel, and the float64 binning of the kernel's own rays."""
+    return compare_image(img, r, rtol=rtol, **kw)
 
 
 @pytest.mark.parametrize("sensor_idx", [0, 1])
@@ -83,7 +47,10 @@ def test_ct3_config1_on_axis_point_source(sensor_idx):
     r = _compare_rays(tel, src, val, "point", sensor_idx)
     img = render(tel, src, val, "point", sensor_idx).cpu().numpy()
     assert img.shape == tuple(tel.sensors[sensor_idx].get_accumulator_shape())
-    _compare_image(img, r, img.shape)
+    # hex camera: the 3.8e5 rays of the on-axis spot fall into a handful of 4 cm pixels; the lid spreads them over
+    # ~1e3 1 mm pixels of a few hundred rays each, so a pixel is "clean" only if none of its rays moved
+    st = _compare_image(img, r, img.shape, min_lit=3 if sensor_idx == 0 else 50, min_flux_share=0.9 if sensor_idx == 0 else 0.2)
+    print("config 1 sensor", sensor_idx, r["stats"], st)
     if sensor_idx == 1:
         # SURVEY section 4 anchor: ~100.7 m^2 shadowed effective area on the lid (MC noise ~0.3 %)
         assert abs(img.sum() - 100.7) < 1.0
@@ -101,7 +68,8 @@ def test_ct5_off_axis_grid(stype, sensor_idx):
     val = np.linspace(0.5, 1.5, len(src)).astype(np.float32)
     r = _compare_rays(tel, src, val, stype, sensor_idx, xy_tol=6e-5)
     img = render(tel, src, val, stype, sensor_idx).cpu().numpy()
-    _compare_image(img, r, img.shape)
+    st = _compare_image(img, r, img.shape, min_lit=9 if sensor_idx == 0 else 1000, min_flux_share=0.9)
+    print("config 2 geometry", stype, sensor_idx, r["stats"], st)
 
 
 def test_culling_is_exact():
@@ -269,7 +237,15 @@ def test_response_matrix_rows_are_single_source_images():
         np.testing.assert_allclose(M[i], img, rtol=2e-6, atol=1e-9)
     total = render(tel, src, val, "parallel", 0).cpu().numpy()
     np.testing.assert_allclose(M.sum(0), total, rtol=2e-5, atol=1e-7)
-    # against the oracle's response matrix (f64), excluding nothing but using a looser per-pixel bound
+    # against the oracle (f64): per ray, then every row per pixel (rays of source i = row i)
+    r = compare_rays(tel, src, val, "parallel", 0)
+    n_m = tel.mirror_groups[0].points.shape[1]
+    src_of_ray = (np.arange(r["v"].size) // n_m) % len(src)                  # facet-major, then source, then sample
+    compared = 0
+    for i in range(len(src)):
+        st = compare_image(M[i], subset_rays(r, src_of_ray == i), min_lit=0, min_flux_share=0.0)
+        compared += st["lit_pixels_compared"]
+    assert compared >= 25                                                   # lit pixels really were compared
     oM = otrace.render_response_matrix(to_oracle_scene(tel), src, val, "parallel", 0, np.float64)
     assert abs(M.sum() - oM.sum()) < 1e-3 * oM.sum()
     # square sensor variant goes through the global-atomic path

@@ -53,3 +53,30 @@ def test_product_key_derivation_matches_oracle(mode):
     assert R.as_key([1, 2]).tolist() == [1, 2]
     with pytest.raises(ValueError):
         R.as_key([1, 2, 3])
+
+
+def test_choice_with_uneven_probabilities_is_distributed_as_p():
+    """``jax.random.choice(key, n, shape, p=p)`` (sample_polygon, utils/sampling.py:53-58) is restated from the
+    upstream source as recalled (cumsum, r = cum[-1] * (1 - U), searchsorted side='left'); no public known-answer
+    vector exists for it offline, so the exact stream stays UNPINNED.  What can be pinned: with
+    very uneven triangle areas the restatement draws each triangle with its probability (4-sigma binomial bound),
+    in both threefry modes, and the resulting points are uniform over the polygon (first moments = centroid)."""
+    from oracle import sample as osample
+    verts = np.float32([[-0.45, -0.30], [0.10, -0.42], [0.48, 0.05], [0.05, 0.40], [-0.35, 0.22]])
+    v0 = verts[0]
+    tri_area = np.array([0.5 * abs((verts[i][0] - v0[0]) * (verts[i + 1][1] - v0[1]) - (verts[i + 1][0] - v0[0]) * (verts[i][1] - v0[1]))
+                         for i in range(1, 4)])
+    p = tri_area / tri_area.sum()
+    assert p.max() / p.min() > 2.0
+    n = 40000
+    for mode in (prng.PARTITIONABLE, prng.LEGACY):
+        idx = prng.choice_p(prng.key(5), p.astype(np.float32), n, mode)
+        freq = np.bincount(idx, minlength=3) / n
+        assert np.all(np.abs(freq - p) < 4.0 * np.sqrt(p * (1 - p) / n)), (freq, p)
+        pts = osample.sample_polygon(prng.key(6), verts, n, mode)
+        # polygon centroid = area-weighted mean of the fan triangles' centroids
+        cen = sum(a * (v0 + verts[i] + verts[i + 1]) / 3.0 for a, i in zip(tri_area, range(1, 4))) / tri_area.sum()
+        assert np.abs(pts.mean(0) - cen).max() < 4.0 * 0.3 / np.sqrt(n)
+    # edge of the convention: U = 0 -> r = cum[-1] -> the last index whose cumulative sum reaches it (never out of range)
+    cum = np.cumsum(p.astype(np.float32), dtype=np.float32)
+    assert np.searchsorted(cum, cum[-1], side="left") == 2

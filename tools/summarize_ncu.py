@@ -1,7 +1,12 @@
 """Summarise an .ncu-rep (read here, without a GPU) into a small text file for profiles/.
 
-usage: python tools/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/NAME.txt [rays_per_launch]
+usage: python tools/summarize_ncu.py gpurun_out/prof.ncu-rep profiles/NAME.txt [rays_per_launch [bench_workload]]
+
+With a bench workload name the first kernel's figures also go to profiles/ncu_figures.json, which bench.py reads for
+roofline.traffic / executed_fp32_frac / issue_slot_util / atomic.
 """
+import json
+from pathlib import Path
 import csv
 import subprocess
 import sys
@@ -41,6 +46,7 @@ def main():
     rows = list(csv.reader(ncu(rep, "--page", "raw", "--csv").splitlines()))
     hdr, units = rows[0], rows[1]
     lines = [f"# ncu summary of {rep}", ""]
+    figures = {}
     for r in rows[2:]:
         name = r[hdr.index("Kernel Name")]
         lines.append(f"## kernel: {name[:160]}")
@@ -57,6 +63,18 @@ def main():
                          for o, m in (("ffma", 2), ("fadd", 1), ("fmul", 1))) * cyc
                 lines.append(f"derived: warp instructions per ray = {wi / rays:.2f}; thread instructions per ray = {wi * tpi / rays:.0f}; "
                              f"executed FP32 flops per ray (FFMA=2) = {fl / rays:.0f}")
+                if len(sys.argv) > 4 and not figures:
+                    num = lambda k: float(vals[k].replace(",", ""))
+                    unit = units[hdr.index("dram__bytes_read.sum")].lower()
+                    scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+                    wunit = units[hdr.index("dram__bytes_write.sum")].lower()
+                    wscale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[wunit]
+                    figures.update(dram_bytes=int(num("dram__bytes_read.sum") * scale + num("dram__bytes_write.sum") * wscale),
+                                   executed_fp32_frac=round(fl / cyc / (148 * 128 * 2), 4),
+                                   issue_slot_util=round(num("smsp__issue_active.avg.pct_of_peak_sustained_active") / 100, 4),
+                                   thread_inst_per_ray=round(wi * tpi / rays, 1),
+                                   shared_atom_inst=int(num("smsp__inst_executed_op_shared_atom.sum")),
+                                   kernel_ms_under_ncu=round(num("gpu__time_duration.sum"), 4), source=out)
             except Exception as e:  # pragma: no cover
                 lines.append(f"derived: n/a ({e})")
         lines.append("")
@@ -78,6 +96,11 @@ def main():
         for a in sorted(agg, key=lambda a: -a[0])[:30]:
             lines.append(f"{100 * a[0] / ti:5.1f}% inst {100 * a[1] / ts:5.1f}% smp  {a[2]}:{a[3]}  {a[4]}")
     open(out, "w").write("\n".join(lines) + "\n")
+    if figures:
+        fj = Path(__file__).resolve().parents[1] / "profiles" / "ncu_figures.json"
+        allf = json.loads(fj.read_text()) if fj.exists() else {}
+        allf[sys.argv[4]] = figures
+        fj.write_text(json.dumps(allf, indent=1) + "\n")
     print("\n".join(lines[:60]))
 
 
