@@ -256,6 +256,8 @@ void fill_sensor(const IactSensor& s, SensDev& d) {
     for (int j = 0; j < 3; ++j) { R[0][j] = cz * a[0][j] - sz * a[1][j]; R[1][j] = sz * a[0][j] + cz * a[1][j]; R[2][j] = a[2][j]; }
     for (int i = 0; i < 3; ++i) { d.pos[i] = s.position[i]; d.u1[i] = R[i][0]; d.u2[i] = R[i][1]; d.nrm[i] = R[i][2]; }
     d.ndotp = d.nrm[0] * d.pos[0] + d.nrm[1] * d.pos[1] + d.nrm[2] * d.pos[2];
+    d.axis_aligned = d.u1[0] == 1.f && d.u1[1] == 0.f && d.u1[2] == 0.f && d.u2[0] == 0.f && d.u2[1] == 1.f && d.u2[2] == 0.f &&
+                     d.nrm[0] == 0.f && d.nrm[1] == 0.f && d.nrm[2] == 1.f;
     d.W = s.width; d.H = s.height;
     d.x0 = (float)s.x0; d.y0 = (float)s.y0; d.dx = (float)s.dx; d.dy = (float)s.dy; d.edge = (float)s.edge_width;
     d.inv_dx = s.dx != 0.0 ? (float)(1.0 / s.dx) : 0.f; d.inv_dy = s.dy != 0.0 ? (float)(1.0 / s.dy) : 0.f;
@@ -324,6 +326,7 @@ size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
     }
     size_t bytes = fl * 4;
     if (d.cull) bytes += (size_t)nwarps * ((n_obs + 1) & ~1) * 2;
+    if (d.cull && d.n_cyl > 0) bytes += (size_t)nwarps * CYL_REC_MAX * CYL_REC * 4 + 16;   // per-warp CylRec records (16-byte aligned)
     return bytes + 16;
 }
 

@@ -275,6 +275,12 @@ struct PixCache {
 #ifndef IACT_HEX_FAST
 #define IACT_HEX_FAST 1
 #endif
+#ifndef IACT_FAR_UNIFORM
+#define IACT_FAR_UNIFORM 1   // one direction per (facet, source) item for point sources with parallax R / D < 1e-9
+#endif
+#ifndef IACT_CYL_RECORDS
+#define IACT_CYL_RECORDS 1   // per-warp CylRec records for items whose rays share their direction
+#endif
 #ifndef IACT_MIN_BLOCKS
 #define IACT_MIN_BLOCKS 4
 #endif
@@ -291,6 +297,7 @@ struct TraceCtx {
     float* hist;
     const short* lut;
     unsigned short* list;
+    float* wrec;              // this warp's CylRec records (CYL_REC_MAX x CYL_REC floats) or nullptr
     bool cull, soft;
 };
 
@@ -316,35 +323,40 @@ __device__ __forceinline__ void trace_setup(const SceneDev& sc, float* smem, Tra
     }
     const int warp = threadIdx.x >> 5;
     cx.list = cx.cull ? reinterpret_cast<unsigned short*>(p) + (size_t)warp * ((n_obs + 1) & ~1) : nullptr;
+    cx.wrec = nullptr;
+    if (cx.cull && cx.ob.n_cyl > 0) {
+        const size_t list_bytes = (size_t)(blockDim.x >> 5) * ((n_obs + 1) & ~1) * sizeof(unsigned short);
+        const uintptr_t base = (reinterpret_cast<uintptr_t>(p) + list_bytes + 15) & ~(uintptr_t)15;
+        cx.wrec = reinterpret_cast<float*>(base) + (size_t)warp * CYL_REC_MAX * CYL_REC;
+    }
     cx.soft = SENS == SENS_SQUARE ? sc.sens.kind == IACT_SENSOR_SOFT_SQUARE : SENS == SENS_SOFT_HEX;
     __syncthreads();
 }
 
-// One ray from table row (a, b) of a facet towards source `src`: shadow of the incoming leg, reflection,
-// optical stages >= 1, sensor plane, binning (or the per-ray debug record at index ri).  Called by all 32
-// lanes; `live` = this lane holds a real ray.
+// One ray from table row (a, b) of a facet: shadow of the incoming leg, reflection, optical stages >= 1, sensor
+// plane, binning (or the per-ray debug record at index ri).  `sd` is the source position, or -- when `uni` -- the
+// direction all rays of this warp item share (parallel sources; far point sources, see trace_item); `n_rec` list
+// entries then have a CylRec record.  Called by all 32 lanes; `live` = this lane holds a real ray.
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
-__device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx, float4 a, float4 b, V3 src, float sval, bool live,
-                                          int n_list_cyl, int n_list, unsigned sub_mask, size_t ri, bool soft7,
+__device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx, float4 a, float4 b, V3 sd, bool uni, float sval, bool live,
+                                          int n_list_cyl, int n_list, int n_rec, unsigned sub_mask, size_t ri, bool soft7,
                                           PixCache& cache, SoftHexCache& scache, float* __restrict__ gout,
                                           float* __restrict__ out_val, int* __restrict__ out_pix) {
     const ObsSmem& ob = cx.ob;
     V3 o = v3(a.x, a.y, a.z);
     const V3 n = v3(b.x, b.y, b.z);
     // render.py:129-133
-    V3 d;
-    if (SRC == IACT_SOURCE_POINT) {
-        d = o - src;
-        d = frsqrt_nr(dot(d, d)) * d;
-    } else {
-        d = src;
+    V3 d = sd;
+    if (SRC == IACT_SOURCE_POINT && !uni) {
+        d = sub_rn(o, sd);
+        d = scale_rn(frsqrt_nr_rn(dot_rn(d, d)), d);
     }
     // render.py:138 shadow of the incoming leg (infinite ray back towards the source)
-    const bool blocked = occluded<SUB>(ob, o, -d, cx.list, n_list_cyl, n_list, sub_mask);
+    const bool blocked = occluded<SUB>(ob, o, -d, cx.list, n_list_cyl, n_list, sub_mask, cx.wrec, n_rec);
     // render.py:140-141, reflection.py:17-19
-    const float c = dot(d, n);
-    d = d - (2.0f * c) * n;
-    float val = blocked ? 0.f : (sval * (-c)) * a.w;         // a.w = 1/weight (transform_kernel)
+    const float c = dot_rn(d, n);
+    d = fma_rn(__fmul_rn(-2.0f, c), n, d);
+    float val = blocked ? 0.f : __fmul_rn(__fmul_rn(sval, -c), a.w);         // a.w = 1/weight (transform_kernel)
     if (STAGES) {
         const float* rec = cx.stage_rec;
         for (int st = 0; st < sc.n_stages; ++st) {
@@ -377,8 +389,7 @@ __device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx
             // rounding (hexagonal.py:32-39) would return it, and the edge rejection (:184-190) sees the identical
             // norm; when that holds for every adding lane the rounding, the table lookup and the slot search are skipped.
             float xg, yg; hex_grid_coords(sc.sens, x, y, xg, yg);
-            const float fdx = fabsf(xg - cache.cx), fdy = fabsf(yg - cache.cy);
-            const float fhn = fmaxf(fdx, 0.5f * fdx + 0.8660254037844386f * fdy) * sc.sens.inv_inradius;
+            const float fhn = hex_norm_rn(sc.sens, __fsub_rn(xg, cache.cx), __fsub_rn(yg, cache.cy));
             if (IACT_HEX_FAST && __all_sync(0xffffffffu, !add || fhn < 0.9999f)) {
                 if (add && !(fhn > sc.sens.edge_thr)) cache.a0 += val;
             } else {
@@ -422,6 +433,24 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
         beam = make_beam<SRC>(__ldg(sc.bounds + f), src);
         n_list = item_list(cx, fl, beam, f, n_list_cyl);
     }
+    // Rays of one item that share their direction: parallel sources, and point sources so far away that the parallax
+    // across the facet (R / D < 1e-9) is below what float32 resolves in `normalize(p - src)` (render.py:130-131: the
+    // subtraction itself rounds p away at that distance).  The direction is then evaluated once, from the facet
+    // centre, and the direction half of the cylinder tests once per (item, candidate) into the warp's records.
+    bool uni = SRC != IACT_SOURCE_POINT;
+    V3 sd = src;
+    if (SRC == IACT_SOURCE_POINT && IACT_FAR_UNIFORM) {
+        const float4 bnd = __ldg(sc.bounds + f);
+        const V3 ac = sub_rn(v3(bnd.x, bnd.y, bnd.z), src);
+        const float n2 = dot_rn(ac, ac);
+        if (bnd.w * bnd.w < 1e-18f * n2 && n2 < 1e37f) { uni = true; sd = scale_rn(frsqrt_nr_rn(n2), ac); }
+    }
+    int n_rec = 0;
+    if (IACT_CYL_RECORDS && uni && cx.wrec) {
+        n_rec = min(n_list_cyl, CYL_REC_MAX);
+        if (lane < n_rec) cyl_record_write(cx.wrec + CYL_REC * lane, cx.ob.cyl + CYL_STRIDE * cx.list[lane], -sd);
+        __syncwarp();
+    }
     const float4* tab = sc.world + ((size_t)f * M) * 2;
     SoftHexCache scache;
     const bool soft7 = SENS == SENS_SOFT_HEX && MODE != MODE_DEBUG && sc.sens.ksize == 1;
@@ -454,7 +483,7 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
             }
         }
         const size_t ri = ((size_t)f * S + s) * M + __float_as_int(b.w);   // debug: original sample index
-        trace_ray<SRC, SENS, MODE, STAGES, SUB>(sc, cx, a, b, src, sval, live, n_list_cyl, n_list, sub_mask, ri, soft7,
+        trace_ray<SRC, SENS, MODE, STAGES, SUB>(sc, cx, a, b, sd, uni, sval, live, n_list_cyl, n_list, n_rec, sub_mask, ri, soft7,
                                                 cache, scache, gout, out_val, out_pix);
     }
     if (SENS == SENS_SOFT_HEX && soft7) scache.flush(sc.sens, cx.lut, cx.hist);
