@@ -47,7 +47,7 @@ class IactSensor(C.Structure):
                 ("grid_offset", C.c_double * 2),
                 ("q_min", C.c_int32), ("r_min", C.c_int32), ("table_q", C.c_int32), ("table_r", C.c_int32),
                 ("n_pixels", C.c_int32), ("lookup", _fp),
-                ("sigma", C.c_double), ("kernel_size", C.c_int32)]
+                ("sigma", C.c_double), ("kernel_size", C.c_int32), ("hex_outer_radius", C.c_double)]
 
 
 class IactScene(C.Structure):
@@ -84,6 +84,10 @@ _SIGNATURES = {
                                          _fp, _fp, _fp, _fp, _fp]),
     "iact_sample_polygon_group": (C.c_int, [_KEY, C.c_int, C.c_int, C.c_int, C.POINTER(IactSurface), C.c_int,
                                             _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
+    "iact_sample_disk_group_rows": (C.c_int, [_KEY, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(IactSurface), _fp,
+                                              _fp, _fp, _fp, _fp, _fp, _fp]),
+    "iact_sample_polygon_group_rows": (C.c_int, [_KEY, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(IactSurface),
+                                                 C.c_int, _fp, _fp, _fp, _fp, _fp, _fp, _fp]),
     "iact_random_normal": (C.c_int, [_KEY, C.c_int, C.c_int, _fp, _fp]),
     "iact_random_uniform": (C.c_int, [_KEY, C.c_int, C.c_int, C.c_float, C.c_float, _fp, _fp]),
     "iact_transform_to_world": (C.c_int, [C.POINTER(IactFacets), C.c_int, _fp, _fp, _fp]),

@@ -28,20 +28,54 @@ class Integrator(ABC):
         return [self.sample_group(g, k) for g, k in zip(mirror_groups, keys[:-1])]
 
 
-class MCIntegrator(Integrator):
-    """Monte-Carlo integrator: ``n_samples`` uniform aperture points per facet (``integrators.py:58-188``)."""
+class SampleStream:
+    """A facet-sample stream that is NOT held in memory: the key, key-derivation mode and length of the
+    ``MCIntegrator(n_samples)`` draw of one mirror group.  Threefry is counter based, so any window of the stream is
+    regenerated bit-identically on demand (``MCIntegrator.sample_rows``); ``render`` walks such a group in L2-sized
+    windows (``core/streaming.py``)."""
 
-    def __init__(self, n_samples: int = 128) -> None:
+    def __init__(self, key, mode: str, n_samples: int) -> None:
+        self.key, self.mode, self.n_samples = R.as_key(key).copy(), mode, int(n_samples)
+
+
+class MCIntegrator(Integrator):
+    """Monte-Carlo integrator: ``n_samples`` uniform aperture points per facet (``integrators.py:58-188``).
+
+    ``stream``: None (default) keeps the sample tables in device memory unless they would exceed
+    ``config.stream_samples_bytes`` (then only the key is kept and ``render`` regenerates the samples window by
+    window); True / False force one or the other.  The random numbers are the same either way."""
+
+    def __init__(self, n_samples: int = 128, stream: bool | None = None) -> None:
         self.n_samples = int(n_samples)
+        self.stream = stream
 
     def sample_group(self, group, key):
+        from .. import config
+        params = group.get_sampling_params()
+        if params["type"] not in ("disk", "polygon"):
+            raise TypeError(f"Unknown MirrorGroup type: {params['type']}")
+        stream = self.stream
+        if stream is None:
+            stream = len(group) * self.n_samples * 72 > config.stream_samples_bytes     # 40 B local + 32 B world per sample
+        if stream:
+            import torch as _t
+            dev, n = group.positions.device, len(group)
+            empty = lambda k: _t.zeros((n, 0, k), dtype=_t.float32, device=dev)
+            return replace(group, points=empty(3), normals=empty(3), perturbation_delta=empty(3), weights=empty(1),
+                           sample_stream=SampleStream(key, R.get_rng_mode(), self.n_samples))
+        return replace(self.sample_rows(group, key, 0, self.n_samples, self.n_samples), sample_stream=None)
+
+    @staticmethod
+    def sample_rows(group, key, first: int, n_rows: int, n_total: int, mode: str | None = None):
+        """Samples ``first .. first + n_rows - 1`` of the ``n_total``-sample stream of ``key`` as a group with
+        materialised (F, n_rows, .) tables (``iact_sample_*_group_rows``)."""
         params = group.get_sampling_params()
         gtype = params["type"]
         if gtype not in ("disk", "polygon"):
             raise TypeError(f"Unknown MirrorGroup type: {gtype}")
         N.require_cuda()
         key = R.as_key(key)
-        F, M = len(group), self.n_samples
+        F, M = len(group), int(n_rows)
         dev = group.positions.device
         pts = torch.empty((F, M, 3), dtype=torch.float32, device=dev)
         nrm = torch.empty((F, M, 3), dtype=torch.float32, device=dev)
@@ -53,14 +87,16 @@ class MCIntegrator(Integrator):
         for i, a in enumerate(group.aspheric.tolist()):
             surf.aspheric[i] = a
         offs = contig(group.offsets.detach())
-        if gtype == "disk":
-            radii = contig(group.radii.detach())
-            rc = N.lib().iact_sample_disk_group(N.key_arg(key), R.mode_code(), F, M, surf, N.ptr(radii), N.ptr(offs),
-                                                N.ptr(pts), N.ptr(nrm), N.ptr(dlt), N.ptr(wts), N.stream_ptr())
-        else:
-            verts = contig(group.vertices.detach())
-            rc = N.lib().iact_sample_polygon_group(N.key_arg(key), R.mode_code(), F, M, surf, group.n_vertices,
-                                                   N.ptr(verts), N.ptr(offs), N.ptr(pts), N.ptr(nrm), N.ptr(dlt),
-                                                   N.ptr(wts), N.stream_ptr())
+        with torch.cuda.device(dev):
+            if gtype == "disk":
+                radii = contig(group.radii.detach())
+                rc = N.lib().iact_sample_disk_group_rows(N.key_arg(key), R.mode_code(mode), F, M, int(first), int(n_total), surf,
+                                                         N.ptr(radii), N.ptr(offs), N.ptr(pts), N.ptr(nrm), N.ptr(dlt),
+                                                         N.ptr(wts), N.stream_ptr())
+            else:
+                verts = contig(group.vertices.detach())
+                rc = N.lib().iact_sample_polygon_group_rows(N.key_arg(key), R.mode_code(mode), F, M, int(first), int(n_total),
+                                                            surf, group.n_vertices, N.ptr(verts), N.ptr(offs), N.ptr(pts),
+                                                            N.ptr(nrm), N.ptr(dlt), N.ptr(wts), N.stream_ptr())
         N.check(rc, "sample_group")
         return replace(group, points=pts, normals=nrm, perturbation_delta=dlt, weights=wts)

@@ -232,6 +232,18 @@ def _stype(source_type) -> int:
 def render(tel, sources, values, source_type="point", sensor_idx: int = 0) -> torch.Tensor:
     """Render sources through the telescope onto a sensor -> image of the sensor's shape."""
     from .autograd import needs_grad, render_with_grad
+    from .streaming import window_plan, iter_windows
+    plan = window_plan(tel)
+    if plan is not None:                      # large draw: L2-sized sample windows, window images added (streaming.py)
+        saved, config.return_numpy = config.return_numpy, False
+        try:
+            out = None
+            for tw in iter_windows(tel, plan):
+                img = render(tw, sources, values, source_type, sensor_idx)
+                out = img if out is None else out + img
+        finally:
+            config.return_numpy = saved
+        return out if out.requires_grad else _out(out)
     if needs_grad(tel, sources, values, sensor_idx):
         return render_with_grad(tel, sources, values, source_type, sensor_idx)
     src, val, dev = _inputs(tel, sources, values)
@@ -250,6 +262,9 @@ def render_debug(tel, sources, values, source_type="point", sensor_idx: int = 0,
     """Raw hits without accumulation -> (points (F*S*M,2), values (F*S*M,)), facet-major then source
     then sample (``render.py:223-268``).  ``return_pixels`` adds the int32 pixel id each ray is
     assigned by the (hard) sensor, -1 = rejected."""
+    if any(getattr(g, "sample_stream", None) is not None for g in tel.mirror_groups):
+        raise NotImplementedError("render_debug needs materialised samples: use MCIntegrator(n_samples, stream=False) "
+                                  "(the per-ray output is n_facets x n_sources x n_samples rows)")
     src, val, dev = _inputs(tel, sources, values)
     keep = []
     sc, _ = build_scene(tel, sensor_idx, keep)
@@ -268,6 +283,18 @@ def render_debug(tel, sources, values, source_type="point", sensor_idx: int = 0,
 @_on_scene_device
 def render_response_matrix(tel, sources, values, source_type="point", sensor_idx: int = 0) -> torch.Tensor:
     """Source-to-pixel response matrix (S, n_pixels): row i is the flattened image of source i alone."""
+    from .streaming import window_plan, iter_windows
+    plan = window_plan(tel)
+    if plan is not None:
+        saved, config.return_numpy = config.return_numpy, False
+        try:
+            out = None
+            for tw in iter_windows(tel, plan):
+                m = render_response_matrix(tw, sources, values, source_type, sensor_idx)
+                out = m if out is None else out.add_(m)
+        finally:
+            config.return_numpy = saved
+        return _out(out)
     src, val, dev = _inputs(tel, sources, values)
     keep = []
     sc, sensor = build_scene(tel, sensor_idx, keep)

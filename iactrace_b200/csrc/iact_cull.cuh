@@ -272,6 +272,7 @@ void fill_sensor(const IactSensor& s, SensDev& d) {
         d.ax_ry = (float)(2.0 / (3.0 * s.hex_size));
     }
     d.inv_inradius = s.hex_inradius != 0.0 ? (float)(1.0 / s.hex_inradius) : 0.f;
+    d.r_out2 = s.hex_outer_radius > 0.0 ? (float)(s.hex_outer_radius * s.hex_outer_radius) : INFINITY;
     d.qmin = s.q_min; d.rmin = s.r_min; d.tq = s.table_q; d.tr = s.table_r; d.npix = s.n_pixels;
     d.lookup = s.lookup; d.sigma = (float)s.sigma; d.ksize = s.kernel_size;
 }
@@ -326,7 +327,9 @@ size_t smem_bytes(const SceneDev& d, int sens, int mode, int nwarps) {
     }
     size_t bytes = fl * 4;
     if (d.cull) bytes += (size_t)nwarps * ((n_obs + 1) & ~1) * 2;
-    if (d.cull && d.n_cyl > 0) bytes += (size_t)nwarps * CYL_REC_MAX * CYL_REC * 4 + 16;   // per-warp CylRec records (16-byte aligned)
+#if IACT_CYL_RECORDS
+    if (d.cull && d.n_cyl > 0) bytes += (size_t)nwarps * CYL_REC_MAX * CYL_REC * 4;        // per-warp CylRec records
+#endif
     return bytes + 16;
 }
 

@@ -14,7 +14,8 @@
 namespace {
 
 struct SampleArgs {
-    Key key; int mode; int F, M;
+    Key key; int mode; int F, M;        // M = rows written per facet
+    int m0, Mtot;                       // ... which are samples m0 .. m0 + M - 1 of a stream of Mtot samples per facet
     SurfDev surf;
     int kind;              // 0 disk, 1 polygon
     int nv;
@@ -26,8 +27,8 @@ __global__ void __launch_bounds__(256) sample_kernel(const SampleArgs a) {
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)a.F * a.M) return;
     const int f = (int)(gid / a.M);
-    const uint32_t m = (uint32_t)(gid % a.M);
-    const uint32_t M = (uint32_t)a.M;
+    const uint32_t m = (uint32_t)a.m0 + (uint32_t)(gid % a.M);         // index in the facet's full stream (random access)
+    const uint32_t M = (uint32_t)a.Mtot;
     const int mode = a.mode;
 
     // integrators.py:108/153 keys = split(key, n_mirrors); :113/158 key_sample, key_perturb = split(mkey)
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) sample_kernel(const SampleArgs a) {
     a.points[o] = x;  a.points[o + 1] = y;  a.points[o + 2] = z;
     a.normals[o] = nx; a.normals[o + 1] = ny; a.normals[o + 2] = nz;
     a.delta[o] = d.x; a.delta[o + 1] = d.y; a.delta[o + 2] = d.z;
-    a.weights[gid] = __fmul_rn(nz / area, (float)a.M);                  // integrators.py:127/175
+    a.weights[gid] = __fmul_rn(nz / area, (float)a.Mtot);               // integrators.py:127/175
 }
 
 __global__ void __launch_bounds__(256) random_kernel(Key key, int mode, int n, int normal, float lo, float hi, float* out) {
@@ -251,16 +252,17 @@ SurfDev make_surf(const IactSurface* s, bool jit_fold) {
     return d;
 }
 
-int launch_sample(const uint32_t key[2], int mode, int F, int M, const IactSurface* surf, int kind, int nv,
+int launch_sample(const uint32_t key[2], int mode, int F, int M, int m0, int Mtot, const IactSurface* surf, int kind, int nv,
                   const float* radii, const float* verts, const float* offsets,
                   float* points, float* normals, float* delta, float* weights, void* stream) {
     IACT_REQUIRE(key && surf && offsets && points && normals && delta && weights, "null pointer");
     IACT_REQUIRE(F >= 0 && M >= 0, "negative size");
+    IACT_REQUIRE(m0 >= 0 && Mtot >= 0 && (long long)m0 + M <= (long long)Mtot, "sample rows outside the stream");
     IACT_REQUIRE(mode == IACT_RNG_PARTITIONABLE || mode == IACT_RNG_LEGACY, "bad rng_mode");
     IACT_REQUIRE(surf->n_aspheric >= 0 && surf->n_aspheric <= IACT_MAX_ASPH, "too many aspheric terms");
     if ((long long)F * M == 0) return IACT_OK;
     SampleArgs a;
-    a.key.a = key[0]; a.key.b = key[1]; a.mode = mode; a.F = F; a.M = M;
+    a.key.a = key[0]; a.key.b = key[1]; a.mode = mode; a.F = F; a.M = M; a.m0 = m0; a.Mtot = Mtot;
     a.surf = make_surf(surf, false);
     a.kind = kind; a.nv = nv; a.radii = radii; a.verts = verts; a.offsets = offsets;
     a.points = points; a.normals = normals; a.delta = delta; a.weights = weights;
@@ -277,7 +279,16 @@ extern "C" int iact_sample_disk_group(const uint32_t key[2], int rng_mode, int n
                                       const IactSurface* surface, const float* radii, const float* offsets,
                                       float* points, float* normals, float* delta, float* weights, void* stream) {
     IACT_REQUIRE(radii, "null radii");
-    return launch_sample(key, rng_mode, n_facets, n_samples, surface, 0, 0, radii, nullptr, offsets,
+    return launch_sample(key, rng_mode, n_facets, n_samples, 0, n_samples, surface, 0, 0, radii, nullptr, offsets,
+                         points, normals, delta, weights, stream);
+}
+
+extern "C" int iact_sample_disk_group_rows(const uint32_t key[2], int rng_mode, int n_facets, int n_rows, int first_sample,
+                                           int n_samples_total, const IactSurface* surface, const float* radii,
+                                           const float* offsets, float* points, float* normals, float* delta, float* weights,
+                                           void* stream) {
+    IACT_REQUIRE(radii, "null radii");
+    return launch_sample(key, rng_mode, n_facets, n_rows, first_sample, n_samples_total, surface, 0, 0, radii, nullptr, offsets,
                          points, normals, delta, weights, stream);
 }
 
@@ -287,8 +298,18 @@ extern "C" int iact_sample_polygon_group(const uint32_t key[2], int rng_mode, in
                                          float* weights, void* stream) {
     IACT_REQUIRE(vertices, "null vertices");
     IACT_REQUIRE(n_vertices >= 3 && n_vertices <= IACT_MAX_POLY, "polygon vertex count out of range");
-    return launch_sample(key, rng_mode, n_facets, n_samples, surface, 1, n_vertices, nullptr, vertices, offsets,
+    return launch_sample(key, rng_mode, n_facets, n_samples, 0, n_samples, surface, 1, n_vertices, nullptr, vertices, offsets,
                          points, normals, delta, weights, stream);
+}
+
+extern "C" int iact_sample_polygon_group_rows(const uint32_t key[2], int rng_mode, int n_facets, int n_rows, int first_sample,
+                                              int n_samples_total, const IactSurface* surface, int n_vertices,
+                                              const float* vertices, const float* offsets, float* points, float* normals,
+                                              float* delta, float* weights, void* stream) {
+    IACT_REQUIRE(vertices, "null vertices");
+    IACT_REQUIRE(n_vertices >= 3 && n_vertices <= IACT_MAX_POLY, "polygon vertex count out of range");
+    return launch_sample(key, rng_mode, n_facets, n_rows, first_sample, n_samples_total, surface, 1, n_vertices, nullptr, vertices,
+                         offsets, points, normals, delta, weights, stream);
 }
 
 static int launch_random(const uint32_t key[2], int mode, int n, int normal, float lo, float hi, float* out, void* stream) {

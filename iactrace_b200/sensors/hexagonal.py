@@ -79,6 +79,9 @@ class HexagonalSensor(_SensorBase):
             table = np.asarray(grid["lookup_table"], np.int32)
             self.q_min, self.r_min = int(grid["q_min"]), int(grid["r_min"])
         self.lookup_table = i32(table)
+        # circle about the grid offset that contains every hexagon (circumradius = hex_size), with float32 slack
+        d = np.asarray(centers, np.float64) - np.asarray(self.grid_offset, np.float64)
+        self.outer_radius = float(np.sqrt((d ** 2).sum(1)).max() + 1.001 * self.hex_size + 1e-5) if len(d) else 0.0
 
     def grid_constants(self) -> dict:
         """The detected grid statics, in a form accepted back by ``grid=``."""
@@ -104,6 +107,7 @@ class HexagonalSensor(_SensorBase):
         s.lookup = N.ptr(lut) if lut.is_cuda else None
         s.sigma = getattr(self, "sigma", 0.0)
         s.kernel_size = getattr(self, "kernel_size", 0)
+        s.hex_outer_radius = getattr(self, "outer_radius", 0.0)
         return s
 
 

@@ -58,6 +58,7 @@ class MirrorGroup:
         self.weights = torch.zeros((n, 0, 1), device=dev)
         self.perturbation_delta = torch.zeros((n, 0, 3), device=dev)
         self.perturbation_scale = torch.zeros(n, device=dev)
+        self.sample_stream = None        # core.integrators.SampleStream when the samples are regenerated on demand
 
     def __len__(self):
         return self.positions.shape[0]

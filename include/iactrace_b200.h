@@ -91,6 +91,10 @@ typedef struct IactSensor {
     /* soft sensors */
     double  sigma;
     int32_t kernel_size;
+    /* hexagonal, optional: radius (about grid_offset) of a circle that contains every hexagon, or 0 = unknown.
+     * Hits outside it belong to no pixel (the lookup of hexagonal.py:155-172 would return -1); the kernel uses it
+     * to skip the cube rounding for rays that miss the camera. */
+    double  hex_outer_radius;
 } IactSensor;
 
 /* Everything a render needs.  `world`/`bounds` come from iact_transform_to_world. */
@@ -157,6 +161,19 @@ int iact_sample_polygon_group(const uint32_t key[2], int rng_mode, int n_facets,
                               const IactSurface* surface, int n_vertices,
                               const float* vertices /*device (F,nv,2)*/, const float* offsets /*device (F,2)*/,
                               float* points, float* normals, float* delta, float* weights, void* stream);
+
+/* The same samplers for a WINDOW of the stream: rows [0, n_rows) of the outputs receive samples
+ * first_sample .. first_sample + n_rows - 1 of the n_samples_total the reference would draw per facet
+ * (threefry is counter based, so any sample is regenerated in isolation, in both key-derivation modes; weights carry
+ * n_samples_total).  This is what lets `render` stream a large MCIntegrator(n_samples) through L2-sized chunks
+ * instead of holding (and re-reading from HBM) an (F, n_samples, 8) table: core/integrators.py:97-188. */
+int iact_sample_disk_group_rows(const uint32_t key[2], int rng_mode, int n_facets, int n_rows, int first_sample,
+                                int n_samples_total, const IactSurface* surface, const float* radii, const float* offsets,
+                                float* points, float* normals, float* delta, float* weights, void* stream);
+int iact_sample_polygon_group_rows(const uint32_t key[2], int rng_mode, int n_facets, int n_rows, int first_sample,
+                                   int n_samples_total, const IactSurface* surface, int n_vertices, const float* vertices,
+                                   const float* offsets, float* points, float* normals, float* delta, float* weights,
+                                   void* stream);
 
 /* jax.random.normal(key,(n,)) / uniform(key,(n,),lo,hi) on the device: used by the
  * host-side parameter edits (telescope/operations.py:186-188,220) and tests. */
