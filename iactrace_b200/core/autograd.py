@@ -76,25 +76,34 @@ class _Render(torch.autograd.Function):
         g_img = contig(g_img.to(torch.float32))
         dev = src.device
         need = ctx.needs_input_grad          # (tel, source_type, sensor_idx, src, val, *leaves)
+        zeros = lambda *shape: torch.zeros(shape, device=dev)
         g_src = torch.zeros_like(src) if need[3] else None
         g_val = torch.zeros_like(val) if need[4] else None
-        g_spos = torch.zeros(3, device=dev)
-        g_srot = torch.zeros(3, device=dev)
+        stage0 = stages.get(0, [])
+        i_sens = 5 + 4 * len(stage0)         # index of the sensor position in `need`
+        # only the gradients somebody asked for are computed: the kernel has a lean instantiation for "facet poses
+        # only" (config 5: an alignment fit w.r.t. rotations) that drops the sensor / source / scale / weight adjoints
+        g_spos = zeros(3) if need[i_sens] else None
+        g_srot = zeros(3) if need[i_sens + 1] else None
         later = [g for k in stages if k != 0 for g in stages[k]]
         n2 = sum(len(g) for g in later)
-        g_mpos = torch.zeros((n2, 3), device=dev) if n2 else None
-        g_mrot = torch.zeros((n2, 3), device=dev) if n2 else None
+        want_stage = n2 > 0 and any(need[i_sens + 2:])
+        g_mpos = zeros(n2, 3) if want_stage else None
+        g_mrot = zeros(n2, 3) if want_stage else None
         grads = []
         keep = []
         sc, _ = build_scene(tel, sensor_idx, keep)
         off = 0
         li = 5                               # index of this group's first leaf in `need`
-        for g in stages.get(0, []):
+        for g in stage0:
             F, M = len(g), g.points.shape[1]
-            gp, gr = torch.zeros((F, 3), device=dev), torch.zeros((F, 3), device=dev)
-            gs = torch.zeros((F,), device=dev)
+            # pose gradients share their accumulators in the kernel: both or neither
+            pose = need[li] or need[li + 1]
+            gp = zeros(F, 3) if pose else None
+            gr = zeros(F, 3) if pose else None
+            gs = zeros(F) if need[li + 2] else None
             # per-sample weight gradients cost one global atomic per ray: only when asked for
-            gw = torch.zeros((F, M, 1), device=dev) if need[li + 3] else None
+            gw = zeros(F, M, 1) if need[li + 3] else None
             li += 4
             if sc is not None and F * M:
                 fa = g._facets_struct(keep)
@@ -114,7 +123,7 @@ class _Render(torch.autograd.Function):
             off += F
         stage_grads, off2 = [], 0
         for g in later:
-            stage_grads += [g_mpos[off2:off2 + len(g)], g_mrot[off2:off2 + len(g)]]
+            stage_grads += ([g_mpos[off2:off2 + len(g)], g_mrot[off2:off2 + len(g)]] if want_stage else [None, None])
             off2 += len(g)
         return (None, None, None, g_src, g_val, *grads, g_spos, g_srot, *stage_grads)
 

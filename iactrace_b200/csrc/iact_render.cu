@@ -146,9 +146,12 @@ __device__ __forceinline__ void splat_soft_hex_warp(const SensDev& se, const LUT
 // for the warp's first base hexagon in registers and the shared histogram is touched 7 times per item.
 // Rays with another base hexagon take the per-tap warp-aggregated path.
 struct SoftHexCache {
-    float qb0, rb0; bool set;
-    float acc[7];
-    __device__ __forceinline__ void reset() { set = false; qb0 = rb0 = 0.f; for (int i = 0; i < 7; ++i) acc[i] = 0.f; }
+    float qb0, rb0, qb1, rb1;          // base hexagons of the two slots (warp-uniform); 1e30 = empty
+    float acc[7], acc1[7];
+    __device__ __forceinline__ void reset() {
+        qb0 = rb0 = qb1 = rb1 = 1e30f;
+        for (int i = 0; i < 7; ++i) acc[i] = acc1[i] = 0.f;
+    }
     // tap order: the 7 (oq, orr) pairs with max(|oq|, |orr|, |oq + orr|) <= 1, oq outer, orr inner
     template <typename LUT>
     __device__ __forceinline__ void add(const SensDev& se, const LUT* lut, bool active, float x, float y, float val, float* hist) {
@@ -156,13 +159,20 @@ struct SoftHexCache {
         const float q = se.ax_qx * xg - se.ax_qy * yg, r = se.ax_ry * yg;
         float qb, rb; hex_round(q, r, qb, rb);
         active = active && (fabsf(qb) < 1e6f) && (fabsf(rb) < 1e6f);
-        const unsigned am = __ballot_sync(0xffffffffu, active);
+        unsigned am = __ballot_sync(0xffffffffu, active);
         if (am == 0u) return;
-        if (!set) {
+        if (qb0 > 1e29f) {
             const int leader = __ffs(am) - 1;
             qb0 = __shfl_sync(0xffffffffu, qb, leader); rb0 = __shfl_sync(0xffffffffu, rb, leader);
-            set = true;
         }
+        bool c0 = active && qb == qb0 && rb == rb0;
+        // a second base hexagon in this item (the spot straddles two cells in about a third of the items)
+        const unsigned other = __ballot_sync(0xffffffffu, active && !c0);
+        if (other != 0u && qb1 > 1e29f) {
+            const int leader = __ffs(other) - 1;
+            qb1 = __shfl_sync(0xffffffffu, qb, leader); rb1 = __shfl_sync(0xffffffffu, rb, leader);
+        }
+        const bool c1 = active && !c0 && qb == qb1 && rb == rb1;
         const float ddx = xg - se.size_sqrt3 * (qb + rb * 0.5f), ddy = yg - se.size_1p5 * rb;
         const float inv_sigma = 1.0f / se.sigma;
         float w[7], wsum = 0.f;
@@ -178,36 +188,38 @@ struct SoftHexCache {
                 w[t] = gauss_half(z * z); wsum += w[t]; ++t;
             }
         const float scale = active ? val / wsum : 0.f;
-        const bool cached = active && qb == qb0 && rb == rb0;
-        if (cached) {
+        const float s0 = c0 ? scale : 0.f, s1 = c1 ? scale : 0.f;
 #pragma unroll
-            for (int i = 0; i < 7; ++i) acc[i] += scale * w[i];
-        }
-        if (__any_sync(0xffffffffu, active && !cached)) {           // rare: a second base hexagon in this item
+        for (int i = 0; i < 7; ++i) { acc[i] = fmaf(s0, w[i], acc[i]); acc1[i] = fmaf(s1, w[i], acc1[i]); }
+        if (__any_sync(0xffffffffu, active && !c0 && !c1)) {        // rare: a third base hexagon in this item
             t = 0;
             for (int oq = -1; oq <= 1; ++oq)
                 for (int orr = -1; orr <= 1; ++orr) {
                     if (oq + orr < -1 || oq + orr > 1) continue;
-                    const int pix = (active && !cached) ? hex_lookup(se, lut, qb + (float)oq, rb + (float)orr) : -1;
+                    const int pix = (active && !c0 && !c1) ? hex_lookup(se, lut, qb + (float)oq, rb + (float)orr) : -1;
                     warp_hist_add(hist, pix, scale * w[t]); ++t;
                 }
         }
     }
     template <typename LUT>
     __device__ __forceinline__ void flush(const SensDev& se, const LUT* lut, float* hist) {
-        if (!set) return;
         const unsigned lane = threadIdx.x & 31u;
-        int t = 0;
-        for (int oq = -1; oq <= 1; ++oq)
-            for (int orr = -1; orr <= 1; ++orr) {
-                if (oq + orr < -1 || oq + orr > 1) continue;
-                float v = acc[t]; ++t;
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                if (lane == 0 && v != 0.f) {
-                    const int pix = hex_lookup(se, lut, qb0 + (float)oq, rb0 + (float)orr);
-                    if (pix >= 0) atomicAdd(hist + pix, v);
+#pragma unroll
+        for (int slot = 0; slot < 2; ++slot) {
+            const float qb = slot ? qb1 : qb0, rb = slot ? rb1 : rb0;
+            if (qb > 1e29f) continue;
+            int t = 0;
+            for (int oq = -1; oq <= 1; ++oq)
+                for (int orr = -1; orr <= 1; ++orr) {
+                    if (oq + orr < -1 || oq + orr > 1) continue;
+                    float v = slot ? acc1[t] : acc[t]; ++t;
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    if (lane == 0 && v != 0.f) {
+                        const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
+                        if (pix >= 0) atomicAdd(hist + pix, v);
+                    }
                 }
-            }
+        }
     }
 };
 
@@ -462,8 +474,10 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
         const float n2 = dot_rn(ac, ac);
         if (bnd.w * bnd.w < 1e-18f * n2 && n2 < 1e37f) { uni = true; sd = scale_rn(frsqrt_nr_rn(n2), ac); }
     }
+    // records pay from three 32-ray iterations per item on (CT3 response matrix at M = 64: 1.125 -> 1.10 ms without) and
+    // not in the stage >= 1 kernels, which are short of registers (Cassegrain: 32.4 -> 31.1 ms without)
     int n_rec = 0;
-    if (IACT_CYL_RECORDS && uni && cx.wrec) {
+    if (IACT_CYL_RECORDS && !STAGES && uni && cx.wrec && m1 - m0 > 64) {
         n_rec = min(n_list_cyl, CYL_REC_MAX);
         if (lane < n_rec) cyl_record_write(cx.wrec + CYL_REC * lane, cx.ob.cyl + CYL_STRIDE * cx.list[lane], -sd);
         __syncwarp();

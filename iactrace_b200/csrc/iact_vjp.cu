@@ -36,15 +36,23 @@ VjpPlan make_vjp_plan(const SceneDev& d, int S, long long resident_warps) {
 
 struct GradsDev {
     float *weights, *values, *sources;
-    float* facc;   // (F,13): dL/dR row-major (9), dL/dpos (3), dL/dscale (1)
+    float* facc;   // (F,13): [0..2] tau (dL/d rotation as an axial vector, see vjp_kernel), [3..8] unused, [9..11] dL/dpos, [12] dL/dscale
     float* sacc;   // 12: dL/d sensor pos (3), dL/d sensor R (9: u1,u2,n as columns -> row-major R)
     float* macc;   // (N2,12) or null: per stage>=1 mirror dL/dR row-major (9), dL/dpos (3)
+};
+
+// Soft hex sensor, one ring of neighbours: the 7 cotangent values around the base hexagon of this lane's previous hit.
+// The hits of one (facet, source) pair mostly share their base hexagon, so the 7 table lookups + loads are done once
+// per run of such hits instead of once per ray (per lane: the ray loop is divergent, no warp election here).
+struct SoftHexG {
+    float qb, rb, g[7];
+    __device__ __forceinline__ void reset() { qb = rb = 1e30f; }
 };
 
 // d(image . G)/d(val) and /d(x, y) for one hit.  Returns false if the hit contributes nothing.
 template <int SENS, typename LUT>
 __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut, const float* __restrict__ G,
-                                               float x, float y, float& dval, float& dx, float& dy) {
+                                               float x, float y, float& dval, float& dx, float& dy, SoftHexG& gc) {
     dx = 0.f; dy = 0.f; dval = 0.f;
     if (se.kind == IACT_SENSOR_SQUARE) {
         const int pix = square_pixel(se, x, y);
@@ -91,7 +99,19 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
     const int K = se.ksize;
     const float inv_sigma = 1.0f / se.sigma;
     float D = 0.f, Nn = 0.f, gx = 0.f, gy = 0.f, wx = 0.f, wy = 0.f;
-    auto tap = [&](int oq, int orr) {
+    if (K == 1 && (qb != gc.qb || rb != gc.rb)) {
+        gc.qb = qb; gc.rb = rb;
+        int t = 0;
+#pragma unroll
+        for (int oq = -1; oq <= 1; ++oq)
+#pragma unroll
+            for (int orr = -1; orr <= 1; ++orr) {
+                if (oq + orr < -1 || oq + orr > 1) continue;
+                const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
+                gc.g[t++] = pix >= 0 ? __ldg(G + pix) : 0.f;
+            }
+    }
+    auto tap = [&](int oq, int orr, int ti) {
         const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
         const float a = ddx - ox, b = ddy - oy;
         const float aa = fabsf(a), ab = fabsf(b);
@@ -105,16 +125,17 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
         const float dhb = (first ? 0.f : 0.8660254037844386f * sb) * se.inv_inradius;
         const float k = -w * z * inv_sigma;                 // dw/dhd
         const float dwx = k * dha, dwy = k * dhb;
-        const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
-        const float g = pix >= 0 ? __ldg(G + pix) : 0.f;
+        float g;
+        if (ti >= 0) g = gc.g[ti];
+        else { const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr); g = pix >= 0 ? __ldg(G + pix) : 0.f; }
         D += w; Nn += g * w; gx += g * dwx; gy += g * dwy; wx += dwx; wy += dwy;
     };
-    if (K == 1) {                                           // the common 7-tap case, fully unrolled
-        tap(-1, 0); tap(-1, 1); tap(0, -1); tap(0, 0); tap(0, 1); tap(1, -1); tap(1, 0);
+    if (K == 1) {                                           // the common 7-tap case, fully unrolled (cached cotangents)
+        tap(-1, 0, 0); tap(-1, 1, 1); tap(0, -1, 2); tap(0, 0, 3); tap(0, 1, 4); tap(1, -1, 5); tap(1, 0, 6);
     } else {
         for (int oq = -K; oq <= K; ++oq)
             for (int orr = -K; orr <= K; ++orr)
-                if (max(max(abs(oq), abs(orr)), abs(oq + orr)) <= K) tap(oq, orr);
+                if (max(max(abs(oq), abs(orr)), abs(oq + orr)) <= K) tap(oq, orr, -1);
     }
     const float invD = frcp_nr(D);
     dval = Nn * invD;
@@ -259,11 +280,17 @@ __device__ __forceinline__ float warp_sum(float v) {
 #ifndef IACT_VJP_MIN_BLOCKS
 #define IACT_VJP_MIN_BLOCKS 2
 #endif
+#ifndef IACT_VJP_MIN_BLOCKS_LEAN
+#define IACT_VJP_MIN_BLOCKS_LEAN 3
+#endif
 #ifndef IACT_VJP_MIN_BLOCKS_STAGES
 #define IACT_VJP_MIN_BLOCKS_STAGES 2
 #endif
-template <int SRC, int SENS, bool STAGES>
-__global__ void __launch_bounds__(256, STAGES ? IACT_VJP_MIN_BLOCKS_STAGES : IACT_VJP_MIN_BLOCKS)
+// FULL = false: only the facet-pose adjoints (dL/dR, dL/dpos -> rotations, positions) are accumulated -- the
+// alignment fit of BASELINE config 5; the sensor-pose, per-source (values, sources), perturbation_scale and
+// per-sample weight adjoints and their registers are compiled out.
+template <int SRC, int SENS, bool STAGES, bool FULL>
+__global__ void __launch_bounds__(256, STAGES ? IACT_VJP_MIN_BLOCKS_STAGES : (FULL ? IACT_VJP_MIN_BLOCKS : IACT_VJP_MIN_BLOCKS_LEAN))
 vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float* __restrict__ sources,
            const float* __restrict__ values, const VjpPlan vp, const FacetLists fl,
            const float* __restrict__ G, const GradsDev gr) {
@@ -295,7 +322,9 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
 
     // Work queue: a unit = (facet, sample part, run of sources), pulled by one warp from a global counter.  The
     // facet's pose is set up and its 13 adjoints are warp-reduced once per unit instead of once per (facet, source).
-    const bool per_source = gr.values != nullptr || gr.sources != nullptr;
+    const bool per_source = FULL && (gr.values != nullptr || gr.sources != nullptr);
+    SoftHexG gcache;
+    gcache.reset();
     for (;;) {
         unsigned long long u = 0;
         if (lane == 0) u = atomicAdd(vp.counter, 1ull);
@@ -310,7 +339,10 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
         const V3 pos = ld3(fa.positions + 3 * f);
         const float scale = __ldg(fa.scale + f);
         const float4 bnd = __ldg(sc.bounds + f);
-        float gR[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        // dL/d(rotation) as an axial vector: every derivative of a rotation matrix is dR/dtheta = [a]x R with a world-frame
+        // axis a, so dL/dtheta = g_o . (a x (o - pos)) + g_nw . (a x nw) = a . tau,
+        // tau = sum (o - pos) x g_o + nw x g_nw  (three accumulators instead of the nine of dL/dR)
+        V3 tau = v3(0.f, 0.f, 0.f);
         V3 g_pos = v3(0.f, 0.f, 0.f);
         float g_scale = 0.f;
         // stage >= 1 mirror adjoints: one register set per lane for the first stage's mirror 0..; rays
@@ -382,20 +414,22 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 const V3 h = oc + t * dc - ps;
                 const float x = dot(h, u1), y = dot(h, u2);
                 float dval, dx, dy;
-                if (!sensor_adjoint<SENS>(se, lut, G, x, y, dval, dx, dy)) continue;
+                if (!sensor_adjoint<SENS>(se, lut, G, x, y, dval, dx, dy, gcache)) continue;
                 // backward: sensor plane
                 const float xb = val * dx, yb = val * dy;           // dL/dx, dL/dy
                 V3 g_o = v3(0.f, 0.f, 0.f), g_r = g_o;
                 if (xb != 0.f || yb != 0.f) {
                     const V3 g_h = xb * u1 + yb * u2;
-                    g_u1 = g_u1 + xb * h; g_u2 = g_u2 + yb * h;
-                    g_ps = g_ps - g_h;
                     g_o = g_h;
                     const float g_t = dot(g_h, dc);
                     g_r = t * g_h;
                     const float gA = g_t * inv_B, gB = -g_t * t * inv_B;
-                    g_ns = g_ns + gA * (ps - oc) + gB * dc;
-                    g_ps = g_ps + gA * ns;
+                    if (FULL) {
+                        g_u1 = g_u1 + xb * h; g_u2 = g_u2 + yb * h;
+                        g_ps = g_ps - g_h;
+                        g_ns = g_ns + gA * (ps - oc) + gB * dc;
+                        g_ps = g_ps + gA * ns;
+                    }
                     g_o = g_o - gA * ns;
                     g_r = g_r + gB * ns;
                 }
@@ -426,8 +460,10 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 }
                 // val = v (-c)/w
                 float g_c = -dval * sval * inv_w;
-                g_val += dval * (-c) * inv_w;
-                if (gr.weights) atomicAdd(gr.weights + (size_t)f * M + m, -dval * val0 * inv_w);
+                if (FULL) {
+                    g_val += dval * (-c) * inv_w;
+                    if (gr.weights) atomicAdd(gr.weights + (size_t)f * M + m, -dval * val0 * inv_w);
+                }
                 // r = d - 2 c n ; c = d.n
                 g_c += -2.0f * dot(g_r, n);
                 V3 g_d = g_r + g_c * n;
@@ -438,16 +474,14 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 if (SRC == IACT_SOURCE_POINT) {
                     const V3 g_a = inv_a * (g_d - dot(g_d, d) * d);
                     g_o = g_o + g_a;
-                    g_src = g_src - g_a;
-                } else {
+                    if (FULL) g_src = g_src - g_a;
+                } else if (FULL) {
                     g_src = g_src + g_d;
                 }
                 // o = R pl + pos ; nw = R (nl + scale dl)
                 g_pos = g_pos + g_o;
-                g_scale += dot(g_nw, mul(R, dl));
-                gR[0] += g_o.x * pl.x + g_nw.x * nq.x; gR[1] += g_o.x * pl.y + g_nw.x * nq.y; gR[2] += g_o.x * pl.z + g_nw.x * nq.z;
-                gR[3] += g_o.y * pl.x + g_nw.y * nq.x; gR[4] += g_o.y * pl.y + g_nw.y * nq.y; gR[5] += g_o.y * pl.z + g_nw.y * nq.z;
-                gR[6] += g_o.z * pl.x + g_nw.z * nq.x; gR[7] += g_o.z * pl.y + g_nw.z * nq.y; gR[8] += g_o.z * pl.z + g_nw.z * nq.z;
+                if (FULL) g_scale += dot(g_nw, mul(R, dl));
+                tau = tau + cross(o - pos, g_o) + cross(nw, g_nw);
             }
             // per-source adjoints
             if (per_source) {
@@ -465,12 +499,13 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
         }
         // per-facet adjoints: warp reduce, one atomic per component
         float* acc = gr.facc + (size_t)f * 13;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { const float v = warp_sum(gR[k]); if (lane == 0 && v != 0.f) atomicAdd(acc + k, v); }
+        { const float v = warp_sum(tau.x); if (lane == 0 && v != 0.f) atomicAdd(acc + 0, v); }
+        { const float v = warp_sum(tau.y); if (lane == 0 && v != 0.f) atomicAdd(acc + 1, v); }
+        { const float v = warp_sum(tau.z); if (lane == 0 && v != 0.f) atomicAdd(acc + 2, v); }
         { const float v = warp_sum(g_pos.x); if (lane == 0 && v != 0.f) atomicAdd(acc + 9, v); }
         { const float v = warp_sum(g_pos.y); if (lane == 0 && v != 0.f) atomicAdd(acc + 10, v); }
         { const float v = warp_sum(g_pos.z); if (lane == 0 && v != 0.f) atomicAdd(acc + 11, v); }
-        { const float v = warp_sum(g_scale); if (lane == 0 && v != 0.f) atomicAdd(acc + 12, v); }
+        if (FULL) { const float v = warp_sum(g_scale); if (lane == 0 && v != 0.f) atomicAdd(acc + 12, v); }
         if (STAGES && gr.macc) {
             // lanes may have cached different mirrors: reduce per distinct id
             unsigned todo = __ballot_sync(0xffffffffu, mreg_id >= 0);
@@ -483,6 +518,7 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
             }
         }
     }
+    if (!FULL) return;
     // sensor adjoints: warp reduce then one atomic per warp and component
     const float sv[12] = {g_ps.x, g_ps.y, g_ps.z,
                           g_u1.x, g_u2.x, g_ns.x, g_u1.y, g_u2.y, g_ns.y, g_u1.z, g_u2.z, g_ns.z};   // dL/dR_s row-major
@@ -530,9 +566,13 @@ __global__ void vjp_finalize_kernel(IactFacets fa, const float* __restrict__ fac
     if (f < fa.n_facets) {
         const float* a = facc + (size_t)f * 13;
         if (out.rotations) {
-            float e[3];
-            euler_adjoint(fa.rotations[3 * f], fa.rotations[3 * f + 1], fa.rotations[3 * f + 2], a, e);
-            for (int k = 0; k < 3; ++k) out.rotations[3 * f + k] += e[k];
+            // R = Rz(rot) Ry(tilt) Rx(tip) (transforms.py:72-106): axes a_tip = Rz Ry x, a_tilt = Rz y, a_rot = z; per degree
+            const float D2R = 0.017453292519943295f;
+            float sy, cy, sz, cz;
+            sincosf(fa.rotations[3 * f + 1] * D2R, &sy, &cy); sincosf(fa.rotations[3 * f + 2] * D2R, &sz, &cz);
+            out.rotations[3 * f + 0] += D2R * (cz * cy * a[0] + sz * cy * a[1] - sy * a[2]);
+            out.rotations[3 * f + 1] += D2R * (-sz * a[0] + cz * a[1]);
+            out.rotations[3 * f + 2] += D2R * a[2];
         }
         if (out.positions) for (int k = 0; k < 3; ++k) out.positions[3 * f + k] += a[9 + k];
         if (out.scale) out.scale[f] += a[12];
@@ -602,13 +642,15 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
         return iact_check_cuda(cudaGetLastError(), "vjp_kernel launch");
     };
     const bool st2 = d.n_stages > 0;
-    if (source_type == IACT_SOURCE_POINT) {
-        if (hex) rc = st2 ? launch(vjp_kernel<IACT_SOURCE_POINT, SENS_HEX, true>) : launch(vjp_kernel<IACT_SOURCE_POINT, SENS_HEX, false>);
-        else     rc = st2 ? launch(vjp_kernel<IACT_SOURCE_POINT, SENS_SQUARE, true>) : launch(vjp_kernel<IACT_SOURCE_POINT, SENS_SQUARE, false>);
-    } else {
-        if (hex) rc = st2 ? launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_HEX, true>) : launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_HEX, false>);
-        else     rc = st2 ? launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_SQUARE, true>) : launch(vjp_kernel<IACT_SOURCE_PARALLEL, SENS_SQUARE, false>);
-    }
+    // lean instantiation: nothing but the facet poses wanted
+    const bool full = grads->scale || grads->weights || grads->values || grads->sources || grads->sensor_position ||
+                      grads->sensor_euler || want_stage;
+#define IACT_VJP_PICK(SRC_, SENS_)                                                                              \
+    (st2 ? (full ? launch(vjp_kernel<SRC_, SENS_, true, true>) : launch(vjp_kernel<SRC_, SENS_, true, false>))  \
+         : (full ? launch(vjp_kernel<SRC_, SENS_, false, true>) : launch(vjp_kernel<SRC_, SENS_, false, false>)))
+    if (source_type == IACT_SOURCE_POINT) rc = hex ? IACT_VJP_PICK(IACT_SOURCE_POINT, SENS_HEX) : IACT_VJP_PICK(IACT_SOURCE_POINT, SENS_SQUARE);
+    else                                  rc = hex ? IACT_VJP_PICK(IACT_SOURCE_PARALLEL, SENS_HEX) : IACT_VJP_PICK(IACT_SOURCE_PARALLEL, SENS_SQUARE);
+#undef IACT_VJP_PICK
     if (rc) return rc;
     const float3 se = make_float3(scene->sensor.euler[0], scene->sensor.euler[1], scene->sensor.euler[2]);
     StageList sl;
