@@ -70,7 +70,7 @@ class IactFacets(C.Structure):
 class IactGrads(C.Structure):
     _fields_ = [("positions", _fp), ("rotations", _fp), ("scale", _fp), ("weights", _fp), ("values", _fp),
                 ("sources", _fp), ("sensor_position", _fp), ("sensor_euler", _fp),
-                ("stage_positions", _fp), ("stage_rotations", _fp)]
+                ("stage_positions", _fp), ("stage_rotations", _fp), ("points", _fp), ("nq", _fp), ("stage_surface", _fp)]
 
 
 _KEY = C.c_uint32 * 2

@@ -81,7 +81,7 @@ class MCIntegrator(Integrator):
         nrm = torch.empty((F, M, 3), dtype=torch.float32, device=dev)
         dlt = torch.empty((F, M, 3), dtype=torch.float32, device=dev)
         wts = torch.empty((F, M, 1), dtype=torch.float32, device=dev)
-        surf = N.IactSurface(group.curvature, group.conic, len(group.aspheric))
+        surf = N.IactSurface(float(group.curvature), float(group.conic), len(group.aspheric))
         if len(group.aspheric) > N.MAX_ASPH:
             raise ValueError(f"at most {N.MAX_ASPH} aspheric terms are supported")
         for i, a in enumerate(group.aspheric.tolist()):

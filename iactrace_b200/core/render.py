@@ -70,11 +70,19 @@ def _world_tables(tel, stage0, later_stages=False):
     return world, bounds, chunks
 
 
+def _scalar(v) -> float:
+    """Surface scalars are Python floats in the reference (surfaces.py:11-12); a fit may hold them as 0-dim tensors."""
+    return float(v.detach()) if isinstance(v, torch.Tensor) else float(v)
+
+
 def _stage_sig(groups):
     ts = []
     for g in groups:
         ts += [g.positions, g.rotations, g.offsets, g.radii if g.kind == "disk" else g.vertices]
-    return (_tensor_sig(ts), tuple((g.curvature, g.conic, tuple(float(a) for a in g.aspheric)) for g in groups))
+        ts += [v for v in (g.curvature, g.conic) if isinstance(v, torch.Tensor)]
+    return (_tensor_sig(ts), tuple((None if isinstance(g.curvature, torch.Tensor) else g.curvature,
+                                    None if isinstance(g.conic, torch.Tensor) else g.conic,
+                                    tuple(float(a) for a in g.aspheric)) for g in groups))
 
 
 def _stage_tables(tel, groups, dev):
@@ -90,7 +98,7 @@ def _stage_tables(tel, groups, dev):
         for i in range(len(g)):
             r = np.zeros(N.MIRROR_REC, np.float32)
             r[0:3], r[3:6], r[6:8] = pos[i], rot[i], off[i]
-            r[8], r[9], r[10] = g.curvature, g.conic, len(asph)
+            r[8], r[9], r[10] = _scalar(g.curvature), _scalar(g.conic), len(asph)
             r[11:11 + len(asph)] = asph
             if g.kind == "disk":
                 r[19], r[20] = 0, float(g.radii[i])

@@ -38,7 +38,8 @@ struct GradsDev {
     float *weights, *values, *sources;
     float* facc;   // (F,13): [0..2] tau (dL/d rotation as an axial vector, see vjp_kernel), [3..8] unused, [9..11] dL/dpos, [12] dL/dscale
     float* sacc;   // 12: dL/d sensor pos (3), dL/d sensor R (9: u1,u2,n as columns -> row-major R)
-    float* macc;   // (N2,12) or null: per stage>=1 mirror dL/dR row-major (9), dL/dpos (3)
+    float* macc;   // (N2,MACC) or null: per stage>=1 mirror dL/dR row-major (9), dL/dpos (3), dL/d(c, k, x0, y0) (4)
+    float *points, *nq;   // (F,M,3) or null: dL/d(local sample point), dL/d(local normal + scale * delta)
 };
 
 // Soft hex sensor, one ring of neighbours: the 7 cotangent values around the base hexagon of this lane's previous hit.
@@ -184,7 +185,9 @@ __device__ __forceinline__ bool stage_select(int n_mirrors, const float* rec, co
 
 // Local geometry of mirror record r at ray parameter t: hit point, unit normal, first and second
 // derivatives of the sag (surfaces.py:25-58; d sag/d r2 = c / (2 s), s = sqrt(1 - (1+k) c^2 r2)).
-struct StageGeom { M33 R; V3 pos, ol, dl, pl, nl; float sx, sy, sxx, sxy, syy, inv_m; };
+struct StageGeom { M33 R; V3 pos, ol, dl, pl, nl; float sx, sy, sxx, sxy, syy, inv_m;
+                   float X, Y, r2, inv_s, c, kc2, x0, y0; const float* rec; };
+#define MACC 16   // floats per stage >= 1 mirror accumulator: dL/dR (9), dL/dpos (3), dL/d(curvature, conic, offset x, offset y)
 
 __device__ __forceinline__ StageGeom stage_geometry(const float* r, V3 o, V3 d, float t) {
     StageGeom g;
@@ -213,6 +216,7 @@ __device__ __forceinline__ StageGeom stage_geometry(const float* r, V3 o, V3 d, 
     g.sx = 2.0f * X * f1; g.sy = 2.0f * Y * f1;
     g.sxx = 2.0f * f1 + 4.0f * X * X * f2; g.sxy = 4.0f * X * Y * f2; g.syy = 2.0f * f1 + 4.0f * Y * Y * f2;
     g.pl = v3(x, y, sag_fast(s, X, Y) - sag_fast(s, x0, y0));
+    g.X = X; g.Y = Y; g.r2 = r2; g.inv_s = inv_s; g.c = s.c; g.kc2 = s.kc2; g.x0 = x0; g.y0 = y0; g.rec = r;
     const V3 m = v3(-g.sx, -g.sy, 1.0f);
     g.inv_m = rsqrtf(dot(m, m));
     g.nl = g.inv_m * m;
@@ -265,6 +269,35 @@ __device__ __forceinline__ void stage_backward(const StageGeom& g, V3 o, V3 d, f
 #pragma unroll
             for (int j = 0; j < 3; ++j) macc[3 * i + j] += a[i] * pl[j] + b[i] * nl[j] + oc3[i] * gol[j] + d3[i] * gdl[j];
         macc[9] += g_p.x - g_o.x; macc[10] += g_p.y - g_o.y; macc[11] += g_p.z - g_o.z;
+        // Surface parameters theta in (curvature c, conic k, offset x0, y0) of surfaces.py:25-45.  With x, y (hence t)
+        // held fixed they enter p_l.z = S(X, Y) - S(x0, y0) and the slopes S_X, S_Y; through the root g(t; theta) = 0 they
+        // move t by dt/dtheta = P / g', P = d p_l.z / d theta.  Hence
+        //   dL/dtheta = (g_pl.z + g_t / g') P_theta + g_sx dS_X/dtheta + g_sy dS_Y/dtheta,
+        // with, for the conic part S = c u / (1 + s), u = r^2, s = sqrt(1 - (1 + k) c^2 u):
+        //   dS/dc = u / (s (1 + s)),  dS/dk = c^3 u^2 / (2 s (1 + s)^2),  d(S_X)/dc = X / s^3,  d(S_X)/dk = X c^3 u / (2 s^3),
+        // and for the offsets (X = x + x0): P = S_X(X, Y) - S_X(x0, y0), dS_X/dx0 = S_XX, dS_Y/dx0 = S_XY (same for y0).
+        const float coef = g_pl.z - k;                               // k = -g_t / g'
+        const float c1 = g.c, c3 = c1 * c1 * c1;
+        auto dS = [&](float u, float inv_s, float& dc, float& dk) {
+            const float sq = 1.0f / inv_s, op = 1.0f + sq;
+            dc = u * inv_s / op;
+            dk = 0.5f * c3 * u * u * inv_s / (op * op);
+        };
+        float dc_h, dk_h, dc_0, dk_0;
+        const float u0 = g.x0 * g.x0 + g.y0 * g.y0;
+        const float inv_s0 = rsqrtf(1.0f - g.kc2 * u0);
+        dS(g.r2, g.inv_s, dc_h, dk_h);
+        dS(u0, inv_s0, dc_0, dk_0);
+        const float is3 = g.inv_s * g.inv_s * g.inv_s;
+        const float dsl_c = is3, dsl_k = 0.5f * c3 * g.r2 * is3;     // d(S_X)/dtheta = X * these
+        macc[12] += coef * (dc_h - dc_0) + (g_sx * g.X + g_sy * g.Y) * dsl_c;
+        macc[13] += coef * (dk_h - dk_0) + (g_sx * g.X + g_sy * g.Y) * dsl_k;
+        // slopes at the offset point, aspheric terms included
+        SurfRef sr;
+        sr.c = g.c; sr.k = g.rec[9]; sr.kc2 = g.kc2; sr.n_asph = (int)g.rec[10]; sr.asph = g.rec + 11; sr.full_scan = false;
+        const float f10 = dsag_dr2_t(sr, u0);
+        macc[14] += coef * (g.sx - 2.0f * g.x0 * f10) + g_sx * g.sxx + g_sy * g.sxy;
+        macc[15] += coef * (g.sy - 2.0f * g.y0 * f10) + g_sx * g.sxy + g_sy * g.syy;
     }
 }
 
@@ -347,7 +380,9 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
         float g_scale = 0.f;
         // stage >= 1 mirror adjoints: one register set per lane for the first stage's mirror 0..; rays
         // that use another (stage, mirror) fall back to direct atomics
-        float mreg[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float mreg[MACC];
+#pragma unroll
+        for (int q = 0; q < MACC; ++q) mreg[q] = 0.f;
         int mreg_id = -1;                                      // flat mirror id the register set belongs to
 
         for (int s = s0; s < s1; ++s) {
@@ -448,9 +483,10 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                             if (flat == mreg_id) {
                                 stage_backward(g, so[k], sd[k], st_t[k], sv[k], g_o, g_r, dval, go2, gd2, gv2, mreg);
                             } else {
-                                float tmp[12] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                                float tmp[MACC];
+                                for (int q = 0; q < MACC; ++q) tmp[q] = 0.f;
                                 stage_backward(g, so[k], sd[k], st_t[k], sv[k], g_o, g_r, dval, go2, gd2, gv2, tmp);
-                                for (int q = 0; q < 12; ++q) if (tmp[q] != 0.f) atomicAdd(gr.macc + (size_t)flat * 12 + q, tmp[q]);
+                                for (int q = 0; q < MACC; ++q) if (tmp[q] != 0.f) atomicAdd(gr.macc + (size_t)flat * MACC + q, tmp[q]);
                             }
                         } else {
                             stage_backward(g, so[k], sd[k], st_t[k], sv[k], g_o, g_r, dval, go2, gd2, gv2, nullptr);
@@ -481,6 +517,16 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 // o = R pl + pos ; nw = R (nl + scale dl)
                 g_pos = g_pos + g_o;
                 if (FULL) g_scale += dot(g_nw, mul(R, dl));
+                if (FULL && gr.points) {                           // per-sample adjoints (surface fits): one atomic per ray, only when asked for
+                    const V3 gl = mulT(R, g_o);
+                    float* gp = gr.points + ((size_t)f * M + m) * 3;
+                    atomicAdd(gp, gl.x); atomicAdd(gp + 1, gl.y); atomicAdd(gp + 2, gl.z);
+                }
+                if (FULL && gr.nq) {
+                    const V3 gl = mulT(R, g_nw);
+                    float* gp = gr.nq + ((size_t)f * M + m) * 3;
+                    atomicAdd(gp, gl.x); atomicAdd(gp + 1, gl.y); atomicAdd(gp + 2, gl.z);
+                }
                 tau = tau + cross(o - pos, g_o) + cross(nw, g_nw);
             }
             // per-source adjoints
@@ -513,7 +559,7 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 const int id = __shfl_sync(0xffffffffu, mreg_id, __ffs(todo) - 1);
                 const bool mine = mreg_id == id;
 #pragma unroll
-                for (int q = 0; q < 12; ++q) { const float v = warp_sum(mine ? mreg[q] : 0.f); if (lane == 0 && v != 0.f) atomicAdd(gr.macc + (size_t)id * 12 + q, v); }
+                for (int q = 0; q < MACC; ++q) { const float v = warp_sum(mine ? mreg[q] : 0.f); if (lane == 0 && v != 0.f) atomicAdd(gr.macc + (size_t)id * MACC + q, v); }
                 todo &= ~__ballot_sync(0xffffffffu, mine);
             }
         }
@@ -554,13 +600,14 @@ __global__ void vjp_finalize_kernel(IactFacets fa, const float* __restrict__ fac
         for (int k = 0; k < sl.n_stages; ++k)
             for (int i = 0; i < sl.st[k].n; ++i, ++flat) {
                 const float* r = sl.st[k].rec + (size_t)i * IACT_MIRROR_REC;
-                const float* a = macc + (size_t)flat * 12;
+                const float* a = macc + (size_t)flat * MACC;
                 if (out.stage_rotations) {
                     float e[3];
                     euler_adjoint(r[3], r[4], r[5], a, e);
                     for (int q = 0; q < 3; ++q) out.stage_rotations[3 * flat + q] += e[q];
                 }
                 if (out.stage_positions) for (int q = 0; q < 3; ++q) out.stage_positions[3 * flat + q] += a[9 + q];
+                if (out.stage_surface) for (int q = 0; q < 4; ++q) out.stage_surface[4 * flat + q] += a[12 + q];
             }
     }
     if (f < fa.n_facets) {
@@ -610,9 +657,9 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     if (d.cull && S >= 4) { rc = run_facet_cull(d, sources, S, source_type, cull_scr, fl, st); if (rc) return rc; }
     int n2 = 0;
     for (int k = 0; k < d.n_stages; ++k) n2 += d.stages[k].n;
-    const bool want_stage = n2 > 0 && (grads->stage_positions || grads->stage_rotations);
+    const bool want_stage = n2 > 0 && (grads->stage_positions || grads->stage_rotations || grads->stage_surface);
     // scratch: the work-queue counter (8 bytes) followed by the adjoint accumulators
-    const size_t acc_floats = 2 + (size_t)d.F * 13 + 12 + (want_stage ? (size_t)n2 * 12 : 0);
+    const size_t acc_floats = 2 + (size_t)d.F * 13 + 12 + (want_stage ? (size_t)n2 * MACC : 0);
     rc = acc_scr.alloc(acc_floats * sizeof(float), st);
     if (rc) return rc;
     IACT_CUDA(cudaMemsetAsync(acc_scr.ptr, 0, acc_floats * sizeof(float), st));
@@ -621,6 +668,7 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     gr.facc = reinterpret_cast<float*>(acc_scr.ptr) + 2;
     gr.sacc = gr.facc + (size_t)d.F * 13;
     gr.macc = want_stage ? gr.sacc + 12 : nullptr;
+    gr.points = grads->points; gr.nq = grads->nq;
 
     const int threads = 256;
     size_t smem = (size_t)obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, d.cull != 0) * 4 + 16;
@@ -643,7 +691,7 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     };
     const bool st2 = d.n_stages > 0;
     // lean instantiation: nothing but the facet poses wanted
-    const bool full = grads->scale || grads->weights || grads->values || grads->sources || grads->sensor_position ||
+    const bool full = grads->points || grads->nq || grads->scale || grads->weights || grads->values || grads->sources || grads->sensor_position ||
                       grads->sensor_euler || want_stage;
 #define IACT_VJP_PICK(SRC_, SENS_)                                                                              \
     (st2 ? (full ? launch(vjp_kernel<SRC_, SENS_, true, true>) : launch(vjp_kernel<SRC_, SENS_, true, false>))  \

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from .. import _native as N
-from .._util import f32, contig
+from .._util import f32, contig, replace
 from ..core.apertures import DiskAperture, PolygonAperture
 from ..core.surfaces import AsphericSurface
 
@@ -72,6 +72,63 @@ class MirrorGroup:
                                           self.normals, self.perturbation_delta, self.weights)]
         keep.extend(t)
         return N.IactFacets(len(self), self.points.shape[1], *[N.ptr(x) for x in t])
+
+    def with_surface(self, curvature=None, conic=None, offsets=None):
+        """This group with other surface parameters (reference ``core/surfaces.py:25-65``); tensors that require grad
+        make ``render`` differentiable w.r.t. them.
+
+        Stage 0: the sample tables are rebuilt as torch functions of (curvature, conic, offsets) -- surface point
+        ``(x, y, sag(x + x0, y + y0) - sag(x0, y0))``, unit normal from the sag gradient, tangent-space perturbation
+        (``reflection.py:22-49``) and weight ``n_z / area * M`` (``integrators.py:125-127``) -- with the drawn aperture
+        coordinates (x, y) and tangent angles held fixed: what ``jax.grad`` through ``MCIntegrator.sample_group`` gives.
+        Stages >= 1 use their surface inside ``render`` (``surfaces.py:67-107``); there the parameters are handed to
+        the kernel, whose VJP differentiates the Newton root implicitly."""
+        c = self.curvature if curvature is None else curvature
+        k = self.conic if conic is None else conic
+        off = self.offsets if offsets is None else f32(offsets).reshape(-1, 2)
+        if self.optical_stage != 0 or self.points.shape[1] == 0:
+            if getattr(self, "sample_stream", None) is not None and self.optical_stage == 0:
+                raise NotImplementedError("with_surface needs materialised samples: MCIntegrator(n, stream=False)")
+            return replace(self, curvature=c, conic=k, offsets=off)
+        dev = self.points.device
+        tt = lambda v: v.to(dev) if isinstance(v, torch.Tensor) else torch.tensor(float(v), dtype=torch.float32, device=dev)
+        ct, kt = tt(c), tt(k)
+        asph = [float(a) for a in (self.aspheric.tolist() if hasattr(self.aspheric, "tolist") else self.aspheric)]
+
+        def sag(x, y):
+            r2 = x * x + y * y
+            z = r2 * ct / (1 + torch.sqrt(1 - (1 + kt) * ct * ct * r2))
+            for i, a in enumerate(asph):
+                z = z + a * r2 ** (2 * i + 2)
+            return z
+
+        def dsag_dr2(r2):
+            f1 = 0.5 * ct / torch.sqrt(1 - (1 + kt) * ct * ct * r2)
+            for i, a in enumerate(asph):
+                f1 = f1 + a * (2 * i + 2) * r2 ** (2 * i + 1)
+            return f1
+
+        old_n, old_d = self.normals.detach(), self.perturbation_delta.detach()
+        x, y = self.points.detach()[..., 0], self.points.detach()[..., 1]
+        x0, y0 = off[:, None, 0], off[:, None, 1]
+        X, Y = x + x0, y + y0
+        pts = torch.stack([x, y, sag(X, Y) - sag(x0, y0)], dim=-1)
+        f1 = dsag_dr2(X * X + Y * Y)
+        m = torch.stack([-2 * X * f1, -2 * Y * f1, torch.ones_like(X)], dim=-1)
+        nrm = m / m.norm(dim=-1, keepdim=True)
+
+        def tangents(n):
+            ref = torch.where((n[..., 2:3].abs() > 0.9), torch.tensor([1.0, 0.0, 0.0], device=dev), torch.tensor([0.0, 0.0, 1.0], device=dev))
+            t1 = torch.cross(n, ref.expand_as(n), dim=-1)
+            t1 = t1 / t1.norm(dim=-1, keepdim=True)
+            return t1, torch.cross(n, t1, dim=-1)
+
+        t1o, t2o = tangents(old_n)
+        th1, th2 = (old_d * t1o).sum(-1, keepdim=True), (old_d * t2o).sum(-1, keepdim=True)     # the drawn N(0,1) angles
+        t1, t2 = tangents(nrm)
+        dlt = th1 * t1 + th2 * t2
+        wts = self.weights * (nrm[..., 2:3] / old_n[..., 2:3])
+        return replace(self, curvature=c, conic=k, offsets=off, points=pts, normals=nrm, perturbation_delta=dlt, weights=wts)
 
     def transform_to_world(self):
         """World-space sample points, perturbed unit normals and weights: (N,M,3),(N,M,3),(N,M,1)

@@ -141,6 +141,11 @@ typedef struct IactGrads {
     float* sensor_euler;   /* device (3,)  */
     float* stage_positions;/* device (N2,3): mirrors of optical stages >= 1, flat in IactScene.stages order */
     float* stage_rotations;/* device (N2,3): Euler degrees                                                  */
+    /* surface fits (core/surfaces.py:25-65) */
+    float* points;         /* device (F,M,3): d/d(local sample point)                        -- one atomic per ray   */
+    float* nq;             /* device (F,M,3): d/d(local normal + perturbation_scale * delta)  -- one atomic per ray   */
+    float* stage_surface;  /* device (N2,4): d/d(curvature, conic, offset x, offset y) of each stage >= 1 mirror,
+                              through the implicit Newton root (intersections.py:290-367)                              */
 } IactGrads;
 
 const char* iact_last_error(void);

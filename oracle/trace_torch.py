@@ -85,7 +85,7 @@ def _accumulate(s, x, y, v):
 
 def _sag_t(x, y, c, k, asph):
     r2 = x * x + y * y
-    z = r2 * c / (1 + torch.sqrt(1 - (1 + k) * c * c * r2))
+    z = r2 * c / (1 + torch.sqrt(torch.as_tensor(1 - (1 + k) * c * c * r2, dtype=DT)))
     for i, a in enumerate(np.asarray(asph, np.float64).tolist()):
         z = z + a * r2 ** (2 * i + 2)
     return z
@@ -93,7 +93,7 @@ def _sag_t(x, y, c, k, asph):
 
 def _dsag_t(x, y, c, k, asph):
     r2 = x * x + y * y
-    f1 = 0.5 * c / torch.sqrt(1 - (1 + k) * c * c * r2)
+    f1 = 0.5 * c / torch.sqrt(torch.as_tensor(1 - (1 + k) * c * c * r2, dtype=DT))
     for i, a in enumerate(np.asarray(asph, np.float64).tolist()):
         f1 = f1 + a * (2 * i + 2) * r2 ** (2 * i + 1)
     return 2 * x * f1, 2 * y * f1
@@ -135,8 +135,12 @@ def _reflect_at_stage(o, d, val, stage_groups, obstructions, stage_leaves=None):
         lv = stage_leaves.get(id(g)) if stage_leaves else None
         pos = lv["positions"][mi] if lv else torch.tensor(g["positions"][mi].astype(np.float64))
         R = euler_to_matrix(lv["rotations"][mi] if lv else torch.tensor(g["rotations"][mi].astype(np.float64)))
-        x0, y0 = float(g["offsets"][mi][0]), float(g["offsets"][mi][1])
-        z0 = _sag_t(torch.tensor(x0, dtype=DT), torch.tensor(y0, dtype=DT), c, k, asph)
+        x0, y0 = torch.tensor(float(g["offsets"][mi][0]), dtype=DT), torch.tensor(float(g["offsets"][mi][1]), dtype=DT)
+        if lv:                                                  # surface parameters as leaves (surfaces.py:25-45)
+            c, k = lv.get("curvature", c), lv.get("conic", k)
+            if "offsets" in lv:
+                x0, y0 = lv["offsets"][mi][0], lv["offsets"][mi][1]
+        z0 = _sag_t(x0, y0, c, k, asph)
         ol = (o - pos) @ R          # R^T (o - pos)
         dl = d @ R
         t0 = torch.from_numpy(np.where(np.isfinite(best_t), best_t, 1.0))
@@ -173,9 +177,9 @@ def render(scene, leaves, sources, values, source_type="point", sensor_idx=0):
         if leaves.get("stage"):
             stage_leaves[id(gr)] = leaves["stage"][i]     # {"positions": (N,3), "rotations": (N,3)} torch leaves
     s = scene["sensors"][sensor_idx]
-    pts = torch.from_numpy(g["points"].astype(np.float64))
-    nrm = torch.from_numpy(g["normals"].astype(np.float64))
-    dlt = torch.from_numpy(g["delta"].astype(np.float64))
+    pts = leaves["points"] if "points" in leaves else torch.from_numpy(g["points"].astype(np.float64))
+    nrm = leaves["normals"] if "normals" in leaves else torch.from_numpy(g["normals"].astype(np.float64))
+    dlt = leaves["delta"] if "delta" in leaves else torch.from_numpy(g["delta"].astype(np.float64))
     F = pts.shape[0]
     Rs = euler_to_matrix(leaves["sensor_rotation"])
     u1, u2, ns = Rs[:, 0], Rs[:, 1], Rs[:, 2]
