@@ -153,28 +153,32 @@ struct SoftHexCache {
         for (int i = 0; i < 7; ++i) acc[i] = acc1[i] = 0.f;
     }
     // tap order: the 7 (oq, orr) pairs with max(|oq|, |orr|, |oq + orr|) <= 1, oq outer, orr inner
+    // The cache outlives the warp items of a unit (the next facet of the same source feeds the same one or two
+    // base hexagons); a new base hexagon takes a free slot, or evicts by flushing both.
     template <typename LUT>
     __device__ __forceinline__ void add(const SensDev& se, const LUT* lut, bool active, float x, float y, float val, float* hist) {
         float xg, yg; hex_grid_coords(se, x, y, xg, yg);
         const float q = se.ax_qx * xg - se.ax_qy * yg, r = se.ax_ry * yg;
         float qb, rb; hex_round(q, r, qb, rb);
         active = active && (fabsf(qb) < 1e6f) && (fabsf(rb) < 1e6f);
-        unsigned am = __ballot_sync(0xffffffffu, active);
-        if (am == 0u) return;
-        if (qb0 > 1e29f) {
-            const int leader = __ffs(am) - 1;
-            qb0 = __shfl_sync(0xffffffffu, qb, leader); rb0 = __shfl_sync(0xffffffffu, rb, leader);
-        }
+        if (!__any_sync(0xffffffffu, active)) return;
         bool c0 = active && qb == qb0 && rb == rb0;
-        // a second base hexagon in this item (the spot straddles two cells in about a third of the items)
-        const unsigned other = __ballot_sync(0xffffffffu, active && !c0);
-        if (other != 0u && qb1 > 1e29f) {
+        bool c1 = active && !c0 && qb == qb1 && rb == rb1;
+        unsigned other = __ballot_sync(0xffffffffu, active && !c0 && !c1);
+        for (int round = 0; round < 2 && other != 0u; ++round) {
             const int leader = __ffs(other) - 1;
-            qb1 = __shfl_sync(0xffffffffu, qb, leader); rb1 = __shfl_sync(0xffffffffu, rb, leader);
+            const float nq = __shfl_sync(0xffffffffu, qb, leader), nr = __shfl_sync(0xffffffffu, rb, leader);
+            if (qb0 > 1e29f) { qb0 = nq; rb0 = nr; }
+            else if (qb1 > 1e29f) { qb1 = nq; rb1 = nr; }
+            else if (round == 0) { flush(se, lut, hist); reset(); qb0 = nq; rb0 = nr; }
+            else break;
+            c0 = active && qb == qb0 && rb == rb0;
+            c1 = active && !c0 && qb == qb1 && rb == rb1;
+            other = __ballot_sync(0xffffffffu, active && !c0 && !c1);
         }
-        const bool c1 = active && !c0 && qb == qb1 && rb == rb1;
         const float ddx = xg - se.size_sqrt3 * (qb + rb * 0.5f), ddy = yg - se.size_1p5 * rb;
-        const float inv_sigma = 1.0f / se.sigma;
+        const float kz = se.inv_inradius / se.sigma;
+        const float nk = -0.72134752044448170368f * kz * kz;          // exp(-z^2 / 2) = 2^(nk m^2), z = m kz (gauss_half)
         float w[7], wsum = 0.f;
         int t = 0;
 #pragma unroll
@@ -184,14 +188,15 @@ struct SoftHexCache {
                 if (oq + orr < -1 || oq + orr > 1) continue;
                 const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
                 const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
-                const float z = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay) * se.inv_inradius * inv_sigma;
-                w[t] = gauss_half(z * z); wsum += w[t]; ++t;
+                const float m = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay);
+                float wt; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(wt) : "f"(nk * (m * m)));
+                w[t] = wt; wsum += wt; ++t;
             }
         const float scale = active ? val / wsum : 0.f;
         const float s0 = c0 ? scale : 0.f, s1 = c1 ? scale : 0.f;
 #pragma unroll
         for (int i = 0; i < 7; ++i) { acc[i] = fmaf(s0, w[i], acc[i]); acc1[i] = fmaf(s1, w[i], acc1[i]); }
-        if (__any_sync(0xffffffffu, active && !c0 && !c1)) {        // rare: a third base hexagon in this item
+        if (other != 0u) {                                          // rare: a third base hexagon within one iteration
             t = 0;
             for (int oq = -1; oq <= 1; ++oq)
                 for (int orr = -1; orr <= 1; ++orr) {
@@ -306,6 +311,9 @@ struct PixCache {
 #endif                               // (a few dozen bytes of spills) beat four at 62 by 2 %; the other instantiations lose 0-6 %
 #ifndef IACT_MIN_BLOCKS_STAGES
 #define IACT_MIN_BLOCKS_STAGES 3
+#endif
+#ifndef IACT_MIN_BLOCKS_SOFT
+#define IACT_MIN_BLOCKS_SOFT 4       // soft hex cameras: two 7-tap register caches per warp
 #endif
 // Everything a warp needs to trace its rays, fixed for the lifetime of the block.
 struct TraceCtx {
@@ -451,7 +459,7 @@ __device__ __forceinline__ int item_list(const TraceCtx& cx, const FacetLists& f
 // One warp item: rays m0..m1 of facet f seen from source s (level-2 list, optional level-3 masks, per-ray trace).
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
 __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& cx, const FacetLists& fl, int S, int s, V3 src, float sval,
-                                           int f, int m0, int m1, PixCache& cache, float* __restrict__ gout,
+                                           int f, int m0, int m1, PixCache& cache, SoftHexCache& scache, float* __restrict__ gout,
                                            float* __restrict__ out_val, int* __restrict__ out_pix) {
     const int lane = threadIdx.x & 31;
     const int M = sc.M;
@@ -483,9 +491,7 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
         __syncwarp();
     }
     const float4* tab = sc.world + ((size_t)f * M) * 2;
-    SoftHexCache scache;
     const bool soft7 = SENS == SENS_SOFT_HEX && MODE != MODE_DEBUG && sc.sens.ksize == 1;
-    if (soft7) scache.reset();
     // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
     const bool sub_beams = SUB && cx.cull && n_list >= 1 && n_list <= 32;
     const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
@@ -517,7 +523,6 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
         trace_ray<SRC, SENS, MODE, STAGES, SUB>(sc, cx, a, b, sd, uni, sval, live, n_list_cyl, n_list, n_rec, sub_mask, ri, soft7,
                                                 cache, scache, gout, out_val, out_pix);
     }
-    if (SENS == SENS_SOFT_HEX && soft7) scache.flush(sc.sens, cx.lut, cx.hist);
     __syncwarp();
 }
 
@@ -528,7 +533,8 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
 // pulled from the same counter (queue.counter == nullptr there selects a static grid-stride split).
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
 __global__ void __launch_bounds__(256, STAGES ? IACT_MIN_BLOCKS_STAGES
-                                              : ((MODE == MODE_RENDER && SENS == SENS_HEX && !SUB) ? IACT_MIN_BLOCKS_RENDER_HEX : IACT_MIN_BLOCKS))
+                                              : ((MODE == MODE_RENDER && SENS == SENS_HEX && !SUB) ? IACT_MIN_BLOCKS_RENDER_HEX
+                                                 : (SENS == SENS_SOFT_HEX ? IACT_MIN_BLOCKS_SOFT : IACT_MIN_BLOCKS)))
 trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
              const LaunchPlan plan, const QueuePlan queue, const FacetLists fl, float* __restrict__ out,
              float* __restrict__ out_val, int* __restrict__ out_pix) {
@@ -543,6 +549,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     // and a new pixel evicts by flushing (PixCache::add); it is emptied before the histogram is read
     PixCache cache;
     cache.reset();
+    SoftHexCache scache;                            // soft hex cameras: same lifetime, emptied at the end of every unit
+    if (SENS == SENS_SOFT_HEX) scache.reset();
 
     if (MODE != MODE_MATRIX) {                    // compile-time: render / debug kernels hold the queue path only (code size)
         const unsigned long long per_src = (unsigned long long)queue.runs * queue.msplit;
@@ -559,7 +567,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             const int f0 = run * queue.facets_per_unit, f1 = min(sc.F, f0 + queue.facets_per_unit);
             const int m0 = part * queue.msize, m1 = min(M, m0 + queue.msize);
             for (int f = f0; f < f1; ++f)
-                trace_item<SRC, SENS, MODE, STAGES, SUB>(sc, cx, fl, plan.S, s, src, sval, f, m0, m1, cache, out, out_val, out_pix);
+                trace_item<SRC, SENS, MODE, STAGES, SUB>(sc, cx, fl, plan.S, s, src, sval, f, m0, m1, cache, scache, out, out_val, out_pix);
+            if (SENS == SENS_SOFT_HEX && MODE != MODE_DEBUG) { scache.flush(sc.sens, cx.lut, cx.hist); scache.reset(); }
         }
     } else {
         const bool pull = MODE == MODE_MATRIX && queue.counter != nullptr;
@@ -582,8 +591,9 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 int fi = wi, part = 0;
                 if (plan.msplit > 1) { fi = wi / plan.msplit; part = wi - fi * plan.msplit; }
                 const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
-                trace_item<SRC, SENS, MODE, STAGES, SUB>(sc, cx, fl, plan.S, s, src, sval, f0 + fi, m0, m1, cache, gout, out_val, out_pix);
+                trace_item<SRC, SENS, MODE, STAGES, SUB>(sc, cx, fl, plan.S, s, src, sval, f0 + fi, m0, m1, cache, scache, gout, out_val, out_pix);
             }
+            if (SENS == SENS_SOFT_HEX) { scache.flush(sc.sens, cx.lut, cx.hist); scache.reset(); }
             if (pull) {                                  // next item: slots alternate, so a slow reader never sees an overwrite
                 slot ^= 1;
                 if (threadIdx.x == 0) s_item[slot] = (long long)atomicAdd(queue.counter, 1ull);

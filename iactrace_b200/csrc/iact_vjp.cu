@@ -368,13 +368,14 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
         const int part = (int)(rest % (unsigned long long)vp.msplit), f = (int)(rest / (unsigned long long)vp.msplit);
         const int s0 = sr * vp.slen, s1 = min(vp.S, s0 + vp.slen);
         const int m0 = part * vp.msize, m1 = min(M, m0 + vp.msize);
-        const M33 R = euler_to_matrix(__ldg(fa.rotations + 3 * f), __ldg(fa.rotations + 3 * f + 1), __ldg(fa.rotations + 3 * f + 2));
+        M33 R;
+        if (FULL) R = euler_to_matrix(__ldg(fa.rotations + 3 * f), __ldg(fa.rotations + 3 * f + 1), __ldg(fa.rotations + 3 * f + 2));
         const V3 pos = ld3(fa.positions + 3 * f);
         const float scale = __ldg(fa.scale + f);
         const float4 bnd = __ldg(sc.bounds + f);
         // dL/d(rotation) as an axial vector: every derivative of a rotation matrix is dR/dtheta = [a]x R with a world-frame
         // axis a, so dL/dtheta = g_o . (a x (o - pos)) + g_nw . (a x nw) = a . tau,
-        // tau = sum (o - pos) x g_o + nw x g_nw  (three accumulators instead of the nine of dL/dR)
+        // tau = sum (o - pos) x g_o + nw x g_nw = sum (o - pos) x g_o + n x g_n  (three accumulators instead of the nine of dL/dR)
         V3 tau = v3(0.f, 0.f, 0.f);
         V3 g_pos = v3(0.f, 0.f, 0.f);
         float g_scale = 0.f;
@@ -398,23 +399,40 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 else            n_list = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, n_list_cyl);
             }
 
+            // far point source (parallax R / D < 1e-9, as trace_item): one direction for the whole facet, and the
+            // adjoint of that direction w.r.t. the ray origin (~1/D) is dropped -- unless d/d(sources) was asked for
+            bool uni = false;
+            V3 sd = src;
+            if (SRC == IACT_SOURCE_POINT && !(FULL && gr.sources)) {
+                const V3 ac = sub_rn(v3(bnd.x, bnd.y, bnd.z), src);
+                const float n2 = dot_rn(ac, ac);
+                if (bnd.w * bnd.w < 1e-18f * n2 && n2 < 1e37f) { uni = true; sd = scale_rn(frsqrt_nr_rn(n2), ac); }
+            }
+
             for (int m = m0 + lane; m < m1; m += 32) {
-                const size_t li = ((size_t)f * M + m) * 3;
-                const V3 pl = ld3(fa.points + li), nl = ld3(fa.normals + li), dl = ld3(fa.delta + li);
-                const float w = __ldg(fa.weights + (size_t)f * M + m);
-                // forward
-                const V3 o = mul(R, pl) + pos;
-                const V3 nq = nl + scale * dl;                      // local perturbed normal
-                const V3 nw = mul(R, nq);
-                const float inv_nw = frsqrt_nr(dot(nw, nw));          // <= 1 ulp, no IEEE slow path (as the forward)
-                const V3 n = inv_nw * nw;
-                V3 d; float inv_a = 0.f;
-                if (SRC == IACT_SOURCE_POINT) { d = o - src; inv_a = frsqrt_nr(dot(d, d)); d = inv_a * d; }
-                else d = src;
+                // forward.  The lean kernel reads the packed world table of the render (world point, unit normal, 1/w:
+                // the same rays, two 128-bit loads); the full one rebuilds them from the local tables it differentiates.
+                V3 o, n, pl, nq, dl, nw;
+                float inv_nw = 0.f, inv_w;
+                if (FULL) {
+                    const size_t li = ((size_t)f * M + m) * 3;
+                    pl = ld3(fa.points + li); dl = ld3(fa.delta + li);
+                    const V3 nl = ld3(fa.normals + li);
+                    o = mul(R, pl) + pos;
+                    nq = nl + scale * dl;                               // local perturbed normal
+                    nw = mul(R, nq);
+                    inv_nw = frsqrt_nr(dot(nw, nw));                    // <= 1 ulp, no IEEE slow path (as the forward)
+                    n = inv_nw * nw;
+                    inv_w = frcp_nr(__ldg(fa.weights + (size_t)f * M + m));
+                } else {
+                    const float4 ta = __ldg(sc.world + 2 * ((size_t)f * M + m)), tb = __ldg(sc.world + 2 * ((size_t)f * M + m) + 1);
+                    o = v3(ta.x, ta.y, ta.z); n = v3(tb.x, tb.y, tb.z); inv_w = ta.w;
+                }
+                V3 d = sd; float inv_a = 0.f;
+                if (SRC == IACT_SOURCE_POINT && !uni) { d = o - src; inv_a = frsqrt_nr(dot(d, d)); d = inv_a * d; }
                 if (occluded(ob, o, -d, list, n_list_cyl, n_list)) continue;
                 const float c = dot(d, n);
                 const V3 r = d - (2.0f * c) * n;
-                const float inv_w = frcp_nr(w);
                 const float val0 = (sval * (-c)) * inv_w;
                 // optical stages >= 1: forward with the state the reverse pass needs
                 V3 so[IACT_MAX_STAGES], sd[IACT_MAX_STAGES];
@@ -441,23 +459,22 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                     }
                 }
                 if (!alive) continue;
-                const float B = dot(dc, ns), ndoto = dot(oc, ns);
+                const bool aa = se.axis_aligned != 0;                 // u1 = x, u2 = y, ns = z: the zero terms drop out
+                const float B = aa ? dc.z : dot(dc, ns), ndoto = aa ? oc.z : dot(oc, ns);
                 if (fabsf(B) < 1e-10f) continue;
                 const float inv_B = frcp_nr(B);
                 const float t = (se.ndotp - ndoto) * inv_B;
                 if (t <= 0.f) continue;
                 const V3 h = oc + t * dc - ps;
-                const float x = dot(h, u1), y = dot(h, u2);
+                const float x = aa ? h.x : dot(h, u1), y = aa ? h.y : dot(h, u2);
                 float dval, dx, dy;
                 if (!sensor_adjoint<SENS>(se, lut, G, x, y, dval, dx, dy, gcache)) continue;
                 // backward: sensor plane
                 const float xb = val * dx, yb = val * dy;           // dL/dx, dL/dy
                 V3 g_o = v3(0.f, 0.f, 0.f), g_r = g_o;
                 if (xb != 0.f || yb != 0.f) {
-                    const V3 g_h = xb * u1 + yb * u2;
-                    g_o = g_h;
-                    const float g_t = dot(g_h, dc);
-                    g_r = t * g_h;
+                    const V3 g_h = aa ? v3(xb, yb, 0.f) : xb * u1 + yb * u2;
+                    const float g_t = aa ? xb * dc.x + yb * dc.y : dot(g_h, dc);
                     const float gA = g_t * inv_B, gB = -g_t * t * inv_B;
                     if (FULL) {
                         g_u1 = g_u1 + xb * h; g_u2 = g_u2 + yb * h;
@@ -465,8 +482,8 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                         g_ns = g_ns + gA * (ps - oc) + gB * dc;
                         g_ps = g_ps + gA * ns;
                     }
-                    g_o = g_o - gA * ns;
-                    g_r = g_r + gB * ns;
+                    if (aa) { g_o = v3(xb, yb, -gA); g_r = v3(t * xb, t * yb, gB); }
+                    else    { g_o = g_h - gA * ns; g_r = t * g_h + gB * ns; }
                 }
                 // backward: stages in reverse order
                 if (STAGES) {
@@ -504,19 +521,23 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 g_c += -2.0f * dot(g_r, n);
                 V3 g_d = g_r + g_c * n;
                 V3 g_n = (-2.0f * c) * g_r + g_c * d;
-                // n = nw/|nw| ; nw = R nq
-                const V3 g_nw = inv_nw * (g_n - dot(g_n, n) * n);
                 // d = a/|a| (point) | src (parallel)
                 if (SRC == IACT_SOURCE_POINT) {
-                    const V3 g_a = inv_a * (g_d - dot(g_d, d) * d);
-                    g_o = g_o + g_a;
-                    if (FULL) g_src = g_src - g_a;
+                    if (!uni) {
+                        const V3 g_a = inv_a * (g_d - dot(g_d, d) * d);
+                        g_o = g_o + g_a;
+                        if (FULL) g_src = g_src - g_a;
+                    }
                 } else if (FULL) {
                     g_src = g_src + g_d;
                 }
-                // o = R pl + pos ; nw = R (nl + scale dl)
+                // o = R pl + pos ; n = nw/|nw| ; nw = R (nl + scale dl)
                 g_pos = g_pos + g_o;
-                if (FULL) g_scale += dot(g_nw, mul(R, dl));
+                V3 g_nw = v3(0.f, 0.f, 0.f);
+                if (FULL) {
+                    g_nw = inv_nw * (g_n - dot(g_n, n) * n);
+                    g_scale += dot(g_nw, mul(R, dl));
+                }
                 if (FULL && gr.points) {                           // per-sample adjoints (surface fits): one atomic per ray, only when asked for
                     const V3 gl = mulT(R, g_o);
                     float* gp = gr.points + ((size_t)f * M + m) * 3;
@@ -527,7 +548,8 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                     float* gp = gr.nq + ((size_t)f * M + m) * 3;
                     atomicAdd(gp, gl.x); atomicAdd(gp + 1, gl.y); atomicAdd(gp + 2, gl.z);
                 }
-                tau = tau + cross(o - pos, g_o) + cross(nw, g_nw);
+                // nw x g_nw = n x g_n (the |nw| cancels and n x n = 0): the world normal is all the rotation adjoint needs
+                tau = tau + cross(o - pos, g_o) + cross(n, g_n);
             }
             // per-source adjoints
             if (per_source) {
