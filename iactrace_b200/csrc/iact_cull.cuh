@@ -275,6 +275,7 @@ void fill_sensor(const IactSensor& s, SensDev& d) {
     d.r_out2 = s.hex_outer_radius > 0.0 ? (float)(s.hex_outer_radius * s.hex_outer_radius) : INFINITY;
     d.qmin = s.q_min; d.rmin = s.r_min; d.tq = s.table_q; d.tr = s.table_r; d.npix = s.n_pixels;
     d.lookup = s.lookup; d.sigma = (float)s.sigma; d.ksize = s.kernel_size;
+    d.soft_nk = (s.sigma > 0.0 && s.hex_inradius > 0.0) ? (float)(-0.72134752044448170368 / (s.hex_inradius * s.hex_inradius * s.sigma * s.sigma)) : 0.f;
 }
 
 int fill_scene(const IactScene* s, SceneDev& d) {

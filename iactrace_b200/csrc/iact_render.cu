@@ -153,32 +153,27 @@ struct SoftHexCache {
         for (int i = 0; i < 7; ++i) acc[i] = acc1[i] = 0.f;
     }
     // tap order: the 7 (oq, orr) pairs with max(|oq|, |orr|, |oq + orr|) <= 1, oq outer, orr inner
-    // The cache outlives the warp items of a unit (the next facet of the same source feeds the same one or two
-    // base hexagons); a new base hexagon takes a free slot, or evicts by flushing both.
     template <typename LUT>
     __device__ __forceinline__ void add(const SensDev& se, const LUT* lut, bool active, float x, float y, float val, float* hist) {
         float xg, yg; hex_grid_coords(se, x, y, xg, yg);
         const float q = se.ax_qx * xg - se.ax_qy * yg, r = se.ax_ry * yg;
         float qb, rb; hex_round(q, r, qb, rb);
         active = active && (fabsf(qb) < 1e6f) && (fabsf(rb) < 1e6f);
-        if (!__any_sync(0xffffffffu, active)) return;
-        bool c0 = active && qb == qb0 && rb == rb0;
-        bool c1 = active && !c0 && qb == qb1 && rb == rb1;
-        unsigned other = __ballot_sync(0xffffffffu, active && !c0 && !c1);
-        for (int round = 0; round < 2 && other != 0u; ++round) {
-            const int leader = __ffs(other) - 1;
-            const float nq = __shfl_sync(0xffffffffu, qb, leader), nr = __shfl_sync(0xffffffffu, rb, leader);
-            if (qb0 > 1e29f) { qb0 = nq; rb0 = nr; }
-            else if (qb1 > 1e29f) { qb1 = nq; rb1 = nr; }
-            else if (round == 0) { flush(se, lut, hist); reset(); qb0 = nq; rb0 = nr; }
-            else break;
-            c0 = active && qb == qb0 && rb == rb0;
-            c1 = active && !c0 && qb == qb1 && rb == rb1;
-            other = __ballot_sync(0xffffffffu, active && !c0 && !c1);
+        unsigned am = __ballot_sync(0xffffffffu, active);
+        if (am == 0u) return;
+        if (qb0 > 1e29f) {
+            const int leader = __ffs(am) - 1;
+            qb0 = __shfl_sync(0xffffffffu, qb, leader); rb0 = __shfl_sync(0xffffffffu, rb, leader);
         }
+        bool c0 = active && qb == qb0 && rb == rb0;
+        // a second base hexagon in this item (the spot straddles two cells in about a third of the items)
+        const unsigned other = __ballot_sync(0xffffffffu, active && !c0);
+        if (other != 0u && qb1 > 1e29f) {
+            const int leader = __ffs(other) - 1;
+            qb1 = __shfl_sync(0xffffffffu, qb, leader); rb1 = __shfl_sync(0xffffffffu, rb, leader);
+        }
+        const bool c1 = active && !c0 && qb == qb1 && rb == rb1;
         const float ddx = xg - se.size_sqrt3 * (qb + rb * 0.5f), ddy = yg - se.size_1p5 * rb;
-        const float kz = se.inv_inradius / se.sigma;
-        const float nk = -0.72134752044448170368f * kz * kz;          // exp(-z^2 / 2) = 2^(nk m^2), z = m kz (gauss_half)
         float w[7], wsum = 0.f;
         int t = 0;
 #pragma unroll
@@ -189,14 +184,14 @@ struct SoftHexCache {
                 const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
                 const float ax = fabsf(ddx - ox), ay = fabsf(ddy - oy);
                 const float m = fmaxf(ax, 0.5f * ax + 0.8660254037844386f * ay);
-                float wt; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(wt) : "f"(nk * (m * m)));
+                float wt; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(wt) : "f"(se.soft_nk * (m * m)));   // exp(-z^2 / 2), z = m / (inradius sigma)
                 w[t] = wt; wsum += wt; ++t;
             }
         const float scale = active ? val / wsum : 0.f;
         const float s0 = c0 ? scale : 0.f, s1 = c1 ? scale : 0.f;
 #pragma unroll
         for (int i = 0; i < 7; ++i) { acc[i] = fmaf(s0, w[i], acc[i]); acc1[i] = fmaf(s1, w[i], acc1[i]); }
-        if (other != 0u) {                                          // rare: a third base hexagon within one iteration
+        if (__any_sync(0xffffffffu, active && !c0 && !c1)) {        // rare: a third base hexagon in this item
             t = 0;
             for (int oq = -1; oq <= 1; ++oq)
                 for (int orr = -1; orr <= 1; ++orr) {
@@ -206,24 +201,34 @@ struct SoftHexCache {
                 }
         }
     }
+    // Both slots at once: the 14 per-lane partial sums are reduced over the warp with a packed butterfly (each step
+    // halves the values a lane carries: 8 + 4 + 2 + 1 + 1 = 16 shuffles instead of 14 x 5), after which the even lanes
+    // hold one total each and add their 14 distinct pixels in a single shared-atomic instruction.
     template <typename LUT>
     __device__ __forceinline__ void flush(const SensDev& se, const LUT* lut, float* hist) {
+        if (qb0 > 1e29f) return;
         const unsigned lane = threadIdx.x & 31u;
+        float v[16];
 #pragma unroll
-        for (int slot = 0; slot < 2; ++slot) {
+        for (int i = 0; i < 7; ++i) { v[i] = acc[i]; v[8 + i] = acc1[i]; }
+        v[7] = 0.f; v[15] = 0.f;
+#pragma unroll
+        for (int n = 8, bit = 16; n >= 1; n >>= 1, bit >>= 1) {
+            const bool up = (lane & bit) != 0;
+#pragma unroll
+            for (int i = 0; i < n; ++i) {
+                const float send = up ? v[i] : v[i + n], keep = up ? v[i + n] : v[i];
+                v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
+        }
+        const float tot = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+        const int idx = (int)(lane >> 1);                             // bits (16, 8, 4, 2) of the lane = value index
+        const int slot = idx >> 3, tap = idx & 7;
+        if ((lane & 1u) == 0u && tap < 7 && tot != 0.f) {
             const float qb = slot ? qb1 : qb0, rb = slot ? rb1 : rb0;
-            if (qb > 1e29f) continue;
-            int t = 0;
-            for (int oq = -1; oq <= 1; ++oq)
-                for (int orr = -1; orr <= 1; ++orr) {
-                    if (oq + orr < -1 || oq + orr > 1) continue;
-                    float v = slot ? acc1[t] : acc[t]; ++t;
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    if (lane == 0 && v != 0.f) {
-                        const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
-                        if (pix >= 0) atomicAdd(hist + pix, v);
-                    }
-                }
+            const int oq = ((0x2211100 >> (4 * tap)) & 0xf) - 1, orr = ((0x1021021 >> (4 * tap)) & 0xf) - 1;
+            const int pix = qb > 1e29f ? -1 : hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
+            if (pix >= 0) atomicAdd(hist + pix, tot);
         }
     }
 };
@@ -459,7 +464,7 @@ __device__ __forceinline__ int item_list(const TraceCtx& cx, const FacetLists& f
 // One warp item: rays m0..m1 of facet f seen from source s (level-2 list, optional level-3 masks, per-ray trace).
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
 __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& cx, const FacetLists& fl, int S, int s, V3 src, float sval,
-                                           int f, int m0, int m1, PixCache& cache, SoftHexCache& scache, float* __restrict__ gout,
+                                           int f, int m0, int m1, PixCache& cache, float* __restrict__ gout,
                                            float* __restrict__ out_val, int* __restrict__ out_pix) {
     const int lane = threadIdx.x & 31;
     const int M = sc.M;
@@ -491,7 +496,9 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
         __syncwarp();
     }
     const float4* tab = sc.world + ((size_t)f * M) * 2;
+    SoftHexCache scache;
     const bool soft7 = SENS == SENS_SOFT_HEX && MODE != MODE_DEBUG && sc.sens.ksize == 1;
+    if (soft7) scache.reset();
     // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
     const bool sub_beams = SUB && cx.cull && n_list >= 1 && n_list <= 32;
     const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
@@ -523,6 +530,7 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
         trace_ray<SRC, SENS, MODE, STAGES, SUB>(sc, cx, a, b, sd, uni, sval, live, n_list_cyl, n_list, n_rec, sub_mask, ri, soft7,
                                                 cache, scache, gout, out_val, out_pix);
     }
+    if (SENS == SENS_SOFT_HEX && soft7) scache.flush(sc.sens, cx.lut, cx.hist);
     __syncwarp();
 }
 
@@ -549,8 +557,6 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
     // and a new pixel evicts by flushing (PixCache::add); it is emptied before the histogram is read
     PixCache cache;
     cache.reset();
-    SoftHexCache scache;                            // soft hex cameras: same lifetime, emptied at the end of every unit
-    if (SENS == SENS_SOFT_HEX) scache.reset();
 
     if (MODE != MODE_MATRIX) {                    // compile-time: render / debug kernels hold the queue path only (code size)
         const unsigned long long per_src = (unsigned long long)queue.runs * queue.msplit;
@@ -567,8 +573,7 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
             const int f0 = run * queue.facets_per_unit, f1 = min(sc.F, f0 + queue.facets_per_unit);
             const int m0 = part * queue.msize, m1 = min(M, m0 + queue.msize);
             for (int f = f0; f < f1; ++f)
-                trace_item<SRC, SENS, MODE, STAGES, SUB>(sc, cx, fl, plan.S, s, src, sval, f, m0, m1, cache, scache, out, out_val, out_pix);
-            if (SENS == SENS_SOFT_HEX && MODE != MODE_DEBUG) { scache.flush(sc.sens, cx.lut, cx.hist); scache.reset(); }
+                trace_item<SRC, SENS, MODE, STAGES, SUB>(sc, cx, fl, plan.S, s, src, sval, f, m0, m1, cache, out, out_val, out_pix);
         }
     } else {
         const bool pull = MODE == MODE_MATRIX && queue.counter != nullptr;
@@ -591,9 +596,8 @@ trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sour
                 int fi = wi, part = 0;
                 if (plan.msplit > 1) { fi = wi / plan.msplit; part = wi - fi * plan.msplit; }
                 const int m0 = part * plan.msize, m1 = min(M, m0 + plan.msize);
-                trace_item<SRC, SENS, MODE, STAGES, SUB>(sc, cx, fl, plan.S, s, src, sval, f0 + fi, m0, m1, cache, scache, gout, out_val, out_pix);
+                trace_item<SRC, SENS, MODE, STAGES, SUB>(sc, cx, fl, plan.S, s, src, sval, f0 + fi, m0, m1, cache, gout, out_val, out_pix);
             }
-            if (SENS == SENS_SOFT_HEX) { scache.flush(sc.sens, cx.lut, cx.hist); scache.reset(); }
             if (pull) {                                  // next item: slots alternate, so a slow reader never sees an overwrite
                 slot ^= 1;
                 if (threadIdx.x == 0) s_item[slot] = (long long)atomicAdd(queue.counter, 1ull);
