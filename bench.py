@@ -427,7 +427,7 @@ def main():
     if rank == 0:
         # ---- the other BASELINE configurations on this GPU: device ms (CUDA events) and end-to-end ms (host buffers)
         workloads = None
-        if not args.no_extras:
+        if not args.no_extras and world == 1:           # one-GPU figures; under torchrun the other ranks would idle
             workloads = {}
             for name in EXTRA_WORKLOADS:
                 x = Workload(name, dev, 0)

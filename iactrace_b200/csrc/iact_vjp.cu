@@ -40,20 +40,32 @@ struct GradsDev {
     float* sacc;   // 12: dL/d sensor pos (3), dL/d sensor R (9: u1,u2,n as columns -> row-major R)
     float* macc;   // (N2,MACC) or null: per stage>=1 mirror dL/dR row-major (9), dL/dpos (3), dL/d(c, k, x0, y0) (4)
     float *points, *nq;   // (F,M,3) or null: dL/d(local sample point), dL/d(local normal + scale * delta)
+    const float* Gn;      // (P,8) or null: cotangent gathered around every pixel (soft hex sensor, one ring)
 };
 
-// Soft hex sensor, one ring of neighbours: the 7 cotangent values around the base hexagon of this lane's previous hit.
-// The hits of one (facet, source) pair mostly share their base hexagon, so the 7 table lookups + loads are done once
-// per run of such hits instead of once per ray (per lane: the ray loop is divergent, no warp election here).
-struct SoftHexG {
-    float qb, rb, g[7];
-    __device__ __forceinline__ void reset() { qb = rb = 1e30f; }
-};
+// Soft hex sensor, one ring of neighbours: the cotangent is pre-gathered per pixel into rows of 8 floats
+// (gather_cotangent_kernel: row p = G at the 7 hexagons around pixel p in tap order, 0 where there is no pixel), so a
+// hit costs one table lookup (its base hexagon) and two 128-bit loads instead of 7 lookups + 7 loads.
+__global__ void __launch_bounds__(256) gather_cotangent_kernel(const SensDev se, const float* __restrict__ G, float* __restrict__ Gn) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= se.tq * se.tr) return;
+    const int pix = se.lookup[p];
+    if (pix < 0) return;
+    const float qb = (float)(p / se.tr + se.qmin), rb = (float)(p % se.tr + se.rmin);
+    int t = 0;
+    for (int oq = -1; oq <= 1; ++oq)
+        for (int orr = -1; orr <= 1; ++orr) {
+            if (oq + orr < -1 || oq + orr > 1) continue;
+            const int nb = hex_lookup(se, se.lookup, qb + (float)oq, rb + (float)orr);
+            Gn[8 * (size_t)pix + t++] = nb >= 0 ? G[nb] : 0.f;
+        }
+    Gn[8 * (size_t)pix + 7] = 0.f;
+}
 
 // d(image . G)/d(val) and /d(x, y) for one hit.  Returns false if the hit contributes nothing.
 template <int SENS, typename LUT>
 __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut, const float* __restrict__ G,
-                                               float x, float y, float& dval, float& dx, float& dy, SoftHexG& gc) {
+                                               float x, float y, float& dval, float& dx, float& dy, const float* __restrict__ Gn) {
     dx = 0.f; dy = 0.f; dval = 0.f;
     if (se.kind == IACT_SENSOR_SQUARE) {
         const int pix = square_pixel(se, x, y);
@@ -98,19 +110,20 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
     if (!(fabsf(qb) < 1e6f && fabsf(rb) < 1e6f)) return false;
     const float ddx = xg - se.size_sqrt3 * (qb + rb * 0.5f), ddy = yg - se.size_1p5 * rb;
     const int K = se.ksize;
-    const float inv_sigma = 1.0f / se.sigma;
     float D = 0.f, Nn = 0.f, gx = 0.f, gy = 0.f, wx = 0.f, wy = 0.f;
-    if (K == 1 && (qb != gc.qb || rb != gc.rb)) {
-        gc.qb = qb; gc.rb = rb;
-        int t = 0;
-#pragma unroll
-        for (int oq = -1; oq <= 1; ++oq)
-#pragma unroll
-            for (int orr = -1; orr <= 1; ++orr) {
-                if (oq + orr < -1 || oq + orr > 1) continue;
-                const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
-                gc.g[t++] = pix >= 0 ? __ldg(G + pix) : 0.f;
-            }
+    // w = exp(-(hd / sigma)^2 / 2) with hd = m / inradius, m = max(|a|, |a|/2 + sqrt(3)/2 |b|) (hexagonal.py:42-47,287):
+    // w = 2^(soft_nk m^2);  dw/d(m^2) = -w / (2 (inradius sigma)^2);  d(m^2)/da = 2a where m = |a|, else sgn(a) m, and
+    // d(m^2)/db = 0 resp. sqrt(3) sgn(b) m  (sgn(0) = 0 as in jnp.abs only matters on a set of measure zero)
+    const float dwm = se.soft_nk * 0.69314718055994530942f;          // soft_nk = -log2(e) / (2 (inradius sigma)^2)
+    float g7[7];
+    bool have = false;
+    if (K == 1 && Gn) {
+        const int pb = hex_lookup(se, lut, qb, rb);
+        if (pb >= 0) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(Gn) + 2 * pb), g1 = __ldg(reinterpret_cast<const float4*>(Gn) + 2 * pb + 1);
+            g7[0] = g0.x; g7[1] = g0.y; g7[2] = g0.z; g7[3] = g0.w; g7[4] = g1.x; g7[5] = g1.y; g7[6] = g1.z;
+            have = true;
+        }
     }
     auto tap = [&](int oq, int orr, int ti) {
         const float ox = se.size_sqrt3 * ((float)oq + (float)orr * 0.5f), oy = se.size_1p5 * (float)orr;
@@ -118,20 +131,17 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
         const float aa = fabsf(a), ab = fabsf(b);
         const float alt = 0.5f * aa + 0.8660254037844386f * ab;
         const bool first = aa >= alt;
-        const float z = fmaxf(aa, alt) * se.inv_inradius * inv_sigma;
-        const float w = gauss_half(z * z);
-        // d hd / d a, d hd / d b  (sign(0) = 0, as jnp.abs)
-        const float sa = a > 0.f ? 1.f : (a < 0.f ? -1.f : 0.f), sb = b > 0.f ? 1.f : (b < 0.f ? -1.f : 0.f);
-        const float dha = (first ? sa : 0.5f * sa) * se.inv_inradius;
-        const float dhb = (first ? 0.f : 0.8660254037844386f * sb) * se.inv_inradius;
-        const float k = -w * z * inv_sigma;                 // dw/dhd
-        const float dwx = k * dha, dwy = k * dhb;
+        const float m = fmaxf(aa, alt);
+        float w; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(w) : "f"(se.soft_nk * (m * m)));
+        const float e = w * dwm;
+        const float dwx = e * (first ? a + a : copysignf(alt, a));
+        const float dwy = e * (first ? 0.f : copysignf(1.7320508075688772f * alt, b));
         float g;
-        if (ti >= 0) g = gc.g[ti];
+        if (ti >= 0 && have) g = g7[ti];
         else { const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr); g = pix >= 0 ? __ldg(G + pix) : 0.f; }
         D += w; Nn += g * w; gx += g * dwx; gy += g * dwy; wx += dwx; wy += dwy;
     };
-    if (K == 1) {                                           // the common 7-tap case, fully unrolled (cached cotangents)
+    if (K == 1) {                                           // the common 7-tap case, fully unrolled
         tap(-1, 0, 0); tap(-1, 1, 1); tap(0, -1, 2); tap(0, 0, 3); tap(0, 1, 4); tap(1, -1, 5); tap(1, 0, 6);
     } else {
         for (int oq = -K; oq <= K; ++oq)
@@ -356,8 +366,6 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
     // Work queue: a unit = (facet, sample part, run of sources), pulled by one warp from a global counter.  The
     // facet's pose is set up and its 13 adjoints are warp-reduced once per unit instead of once per (facet, source).
     const bool per_source = FULL && (gr.values != nullptr || gr.sources != nullptr);
-    SoftHexG gcache;
-    gcache.reset();
     for (;;) {
         unsigned long long u = 0;
         if (lane == 0) u = atomicAdd(vp.counter, 1ull);
@@ -468,7 +476,7 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 const V3 h = oc + t * dc - ps;
                 const float x = aa ? h.x : dot(h, u1), y = aa ? h.y : dot(h, u2);
                 float dval, dx, dy;
-                if (!sensor_adjoint<SENS>(se, lut, G, x, y, dval, dx, dy, gcache)) continue;
+                if (!sensor_adjoint<SENS>(se, lut, G, x, y, dval, dx, dy, gr.Gn)) continue;
                 // backward: sensor plane
                 const float xb = val * dx, yb = val * dy;           // dL/dx, dL/dy
                 V3 g_o = v3(0.f, 0.f, 0.f), g_r = g_o;
@@ -691,6 +699,17 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     gr.sacc = gr.facc + (size_t)d.F * 13;
     gr.macc = want_stage ? gr.sacc + 12 : nullptr;
     gr.points = grads->points; gr.nq = grads->nq;
+    gr.Gn = nullptr;
+    Scratch gn_scr;
+    if (d.sens.kind == IACT_SENSOR_SOFT_HEX && d.sens.ksize == 1) {
+        rc = gn_scr.alloc((size_t)d.sens.npix * 8 * sizeof(float), st);
+        if (rc) return rc;
+        const int cells = d.sens.tq * d.sens.tr;
+        gather_cotangent_kernel<<<(cells + 255) / 256, 256, 0, st>>>(d.sens, cotangent, reinterpret_cast<float*>(gn_scr.ptr));
+        iact_count_launch();
+        IACT_CUDA(cudaGetLastError());
+        gr.Gn = reinterpret_cast<const float*>(gn_scr.ptr);
+    }
 
     const int threads = 256;
     size_t smem = (size_t)obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, d.cull != 0) * 4 + 16;
