@@ -116,13 +116,19 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
     // d(m^2)/db = 0 resp. sqrt(3) sgn(b) m  (sgn(0) = 0 as in jnp.abs only matters on a set of measure zero)
     const float dwm = se.soft_nk * 0.69314718055994530942f;          // soft_nk = -log2(e) / (2 (inradius sigma)^2)
     float g7[7];
-    bool have = false;
-    if (K == 1 && Gn) {
-        const int pb = hex_lookup(se, lut, qb, rb);
+    if (K == 1) {
+        const int pb = Gn ? hex_lookup(se, lut, qb, rb) : -1;
         if (pb >= 0) {
             const float4 g0 = __ldg(reinterpret_cast<const float4*>(Gn) + 2 * pb), g1 = __ldg(reinterpret_cast<const float4*>(Gn) + 2 * pb + 1);
             g7[0] = g0.x; g7[1] = g0.y; g7[2] = g0.z; g7[3] = g0.w; g7[4] = g1.x; g7[5] = g1.y; g7[6] = g1.z;
-            have = true;
+        } else {                                            // base hexagon is no pixel (camera rim, holes): tap by tap
+            int t = 0;
+            for (int oq = -1; oq <= 1; ++oq)
+                for (int orr = -1; orr <= 1; ++orr) {
+                    if (oq + orr < -1 || oq + orr > 1) continue;
+                    const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr);
+                    g7[t++] = pix >= 0 ? __ldg(G + pix) : 0.f;
+                }
         }
     }
     auto tap = [&](int oq, int orr, int ti) {
@@ -137,7 +143,7 @@ __device__ __forceinline__ bool sensor_adjoint(const SensDev& se, const LUT* lut
         const float dwx = e * (first ? a + a : copysignf(alt, a));
         const float dwy = e * (first ? 0.f : copysignf(1.7320508075688772f * alt, b));
         float g;
-        if (ti >= 0 && have) g = g7[ti];
+        if (ti >= 0) g = g7[ti];                            // compile-time: the 7-tap instantiation has no branch here
         else { const int pix = hex_lookup(se, lut, qb + (float)oq, rb + (float)orr); g = pix >= 0 ? __ldg(G + pix) : 0.f; }
         D += w; Nn += g * w; gx += g * dwx; gy += g * dwy; wx += dwx; wy += dwy;
     };
