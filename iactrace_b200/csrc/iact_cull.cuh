@@ -22,7 +22,8 @@ struct QueuePlan { int facets_per_unit, runs, msplit, msize; long long n_units; 
 
 // Level-1 culling output: per facet a list of primitive ids (cylinders first) and its two counts;
 // count.x < 0 means "no facet-level culling for this facet" (degenerate beam): use every primitive.
-struct FacetLists { const unsigned short* ids; const int2* count; int stride; };
+struct FacetLists { const unsigned short* ids; const int2* count; int stride;
+                    unsigned long long* counter; };   // work-queue counter zeroed by facet_cull_kernel (nullptr: none)
 
 struct Beam { V3 c, u; float R, invD, spread; bool ok; };
 
@@ -178,10 +179,15 @@ __device__ __forceinline__ bool occluded_leg_culled(const ObsSmem& ob, V3 o, V3 
 // ---------------------------------------------------------------- level-1 culling: facet x all sources
 // One warp per facet: bounding cone of the directions towards all sources, then one pass over the
 // primitives.  Writes ids[f*stride ..] and count[f] = (n_cyl_kept, n_total_kept) or (-1,-1).
+// Also zeroes the work-queue counter of the trace kernel that follows and (render on a hex camera) the output image:
+// two memset launches less per render, which matters for the 0.5 ms jobs of an 8-way source split.
 template <int SRC>
 __global__ void __launch_bounds__(256) facet_cull_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources,
-                                                         int S, unsigned short* __restrict__ ids, int2* __restrict__ count, int stride) {
+                                                         int S, unsigned short* __restrict__ ids, int2* __restrict__ count, int stride,
+                                                         unsigned long long* __restrict__ counter, float* __restrict__ zero, size_t n_zero) {
     extern __shared__ __align__(16) float smem[];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0ull;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += (size_t)gridDim.x * blockDim.x) zero[i] = 0.f;
     ObsSmem ob;
     stage_obstructions(sc, smem, ob, true);
     __syncthreads();
@@ -357,27 +363,29 @@ struct Scratch {
 };
 
 // Launch level-1 culling into `scr`; fills `fl`.
-int run_facet_cull(const SceneDev& d, const float* sources, int S, int source_type, Scratch& scr, FacetLists& fl, cudaStream_t st) {
-    fl.ids = nullptr; fl.count = nullptr; fl.stride = 0;
+int run_facet_cull(const SceneDev& d, const float* sources, int S, int source_type, Scratch& scr, FacetLists& fl, cudaStream_t st,
+                   float* zero = nullptr, size_t n_zero = 0) {
+    fl.ids = nullptr; fl.count = nullptr; fl.stride = 0; fl.counter = nullptr;
     if (!d.cull) return IACT_OK;
     const int n_obs = d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri;
     const int stride = (n_obs + 7) & ~7;
-    const size_t count_bytes = ((size_t)d.F * sizeof(int2) + 15) & ~(size_t)15;
+    const size_t count_bytes = 16 + (((size_t)d.F * sizeof(int2) + 15) & ~(size_t)15);   // [0..8) = the work-queue counter
     int rc = scr.alloc(count_bytes + (size_t)d.F * stride * sizeof(unsigned short), st);
     if (rc) return rc;
-    int2* count = reinterpret_cast<int2*>(scr.ptr);
+    unsigned long long* counter = reinterpret_cast<unsigned long long*>(scr.ptr);
+    int2* count = reinterpret_cast<int2*>(reinterpret_cast<char*>(scr.ptr) + 16);
     unsigned short* ids = reinterpret_cast<unsigned short*>(reinterpret_cast<char*>(scr.ptr) + count_bytes);
     const size_t smem = (size_t)obstruction_floats(d.n_cyl, d.n_box, d.n_sph, d.n_obox, d.n_tri, true) * 4 + 16;
     if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
     const int blocks = std::max(1, std::min((d.F + 7) / 8, sm_count() * 2));
     auto launch = [&](auto kern) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<blocks, 256, smem, st>>>(d, sources, S, ids, count, stride);
+        kern<<<blocks, 256, smem, st>>>(d, sources, S, ids, count, stride, counter, zero, n_zero);
     };
     if (source_type == IACT_SOURCE_POINT) launch(facet_cull_kernel<IACT_SOURCE_POINT>);
     else launch(facet_cull_kernel<IACT_SOURCE_PARALLEL>);
     iact_count_launch();
-    fl.ids = ids; fl.count = count; fl.stride = stride;
+    fl.ids = ids; fl.count = count; fl.stride = stride; fl.counter = counter;
     return iact_check_cuda(cudaGetLastError(), "facet_cull_kernel launch");
 }
 
@@ -385,11 +393,14 @@ int run_facet_cull(const SceneDev& d, const float* sources, int S, int source_ty
 LaunchPlan make_plan(const SceneDev& d, int S, int mode) {
     LaunchPlan p;
     p.S = S;
-    const long long target = (long long)sm_count() * 16;          // block items wanted for balance
-    int n_chunks = 1;
-    if (S < target) n_chunks = (int)std::min<long long>(d.F, (target + S - 1) / std::max(S, 1));
     const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
-    if (mode == MODE_MATRIX && hex && S >= 2 * sm_count()) n_chunks = 1;   // plain-store flush, no atomics
+    // block items wanted for balance.  Response matrix on a hex camera: with at least 8 rows per SM a block owns whole
+    // rows (plain-store flush, no atomics, no memset); with fewer rows (a row shard of a multi-GPU run: 512 rows on 148
+    // SMs left 13 % of the block slots empty and a long tail) the rows are cut into facet chunks, ~48 items per SM
+    const bool whole_rows = mode == MODE_MATRIX && hex && S >= 8 * sm_count();
+    const long long target = (long long)sm_count() * ((mode == MODE_MATRIX && hex) ? 48 : 16);
+    int n_chunks = 1;
+    if (S < target && !whole_rows) n_chunks = (int)std::min<long long>(d.F, (target + S - 1) / std::max(S, 1));
     n_chunks = std::max(n_chunks, 1);
     p.chunk_facets = (d.F + n_chunks - 1) / n_chunks;
     p.n_chunks = (d.F + p.chunk_facets - 1) / p.chunk_facets;
@@ -402,14 +413,14 @@ LaunchPlan make_plan(const SceneDev& d, int S, int mode) {
     return p;
 }
 
-// Units of the render / debug work queue: about 64 per resident warp when the job is large (short tail, one
+// Units of the render / debug work queue: about 16 per resident warp when the job is large (short tail, one
 // atomic per ~1e4 warp instructions); small jobs are split along the samples so that every warp gets work.
 #ifndef IACT_QUEUE_FPU
 #define IACT_QUEUE_FPU 8
 #endif
 #ifndef IACT_QUEUE_UNITS
-#define IACT_QUEUE_UNITS 64
-#endif
+#define IACT_QUEUE_UNITS 16          // 64 made 5920 warps pull 4.5e5 units from one counter in 0.5 ms on a 512-source job
+#endif                               // (same-address atomics at 1 per ns): 634 -> 561 us; no change at 4096 sources
 QueuePlan make_queue_plan(const SceneDev& d, int S, long long resident_warps) {
     QueuePlan q;
     const long long pairs = (long long)S * d.F;

@@ -723,13 +723,15 @@ int launch_kernel(K kern, const SceneDev& d, const float* sources, const float* 
     QueuePlan q = make_queue_plan(d, plan.S, max_blocks * (threads / 32));
     long long blocks = plan.n_items;
     Scratch ctr;
-    {
+    if (fl.counter) {
+        q.counter = fl.counter;                                   // zeroed by facet_cull_kernel
+    } else {
         int rc = ctr.alloc(sizeof(unsigned long long), stream);
         if (rc) return rc;
         IACT_CUDA(cudaMemsetAsync(ctr.ptr, 0, sizeof(unsigned long long), stream));
         q.counter = reinterpret_cast<unsigned long long*>(ctr.ptr);
-        if (MODE != MODE_MATRIX) blocks = (q.n_units + threads / 32 - 1) / (threads / 32);
     }
+    if (MODE != MODE_MATRIX) blocks = (q.n_units + threads / 32 - 1) / (threads / 32);
     const unsigned grid = (unsigned)std::max(1LL, std::min(blocks, max_blocks));
     kern<<<grid, threads, smem, stream>>>(d, sources, values, plan, q, fl, out, out_val, out_pix);
     iact_count_launch();
@@ -788,7 +790,8 @@ int run(const IactScene* scene, const float* sources, const float* values, int S
         IACT_CUDA(cudaMemsetAsync(acc64.ptr, 0, npix * sizeof(double), st));
         out = reinterpret_cast<float*>(acc64.ptr);
     } else if (mode == MODE_RENDER) {
-        IACT_CUDA(cudaMemsetAsync(out, 0, npix * sizeof(float), st));        // render.py:198-199,218
+        if (!(hex && !empty && d.cull && S >= 4))                            // else: zeroed by facet_cull_kernel below
+            IACT_CUDA(cudaMemsetAsync(out, 0, npix * sizeof(float), st));    // render.py:198-199,218
     } else if (mode == MODE_MATRIX) {
         if (empty || !(hex && plan.n_chunks == 1)) IACT_CUDA(cudaMemsetAsync(out, 0, (size_t)S * npix * sizeof(float), st));
     } else {
@@ -799,9 +802,13 @@ int run(const IactScene* scene, const float* sources, const float* values, int S
     plan.n_items = (long long)S * plan.n_chunks;
     Scratch scr;
     FacetLists fl;
-    fl.ids = nullptr; fl.count = nullptr; fl.stride = 0;
+    fl.ids = nullptr; fl.count = nullptr; fl.stride = 0; fl.counter = nullptr;
     // level-1 lists pay off once a facet is seen from several sources
-    if (d.cull && S >= 4) { rc = run_facet_cull(d, sources, S, source_type, scr, fl, st); if (rc) return rc; }
+    if (d.cull && S >= 4) {
+        const bool zero_image = mode == MODE_RENDER && hex;
+        rc = run_facet_cull(d, sources, S, source_type, scr, fl, st, zero_image ? out : nullptr, zero_image ? npix : 0);
+        if (rc) return rc;
+    }
     switch (mode) {
         case MODE_RENDER:
             rc = launch_src<MODE_RENDER>(source_type, d, sources, values, plan, fl, out, out_val, out_pix, st);

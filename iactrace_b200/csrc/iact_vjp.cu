@@ -689,7 +689,7 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     const bool hex = d.sens.kind == IACT_SENSOR_HEX || d.sens.kind == IACT_SENSOR_SOFT_HEX;
     Scratch cull_scr, acc_scr;
     FacetLists fl;
-    fl.ids = nullptr; fl.count = nullptr; fl.stride = 0;
+    fl.ids = nullptr; fl.count = nullptr; fl.stride = 0; fl.counter = nullptr;
     if (d.cull && S >= 4) { rc = run_facet_cull(d, sources, S, source_type, cull_scr, fl, st); if (rc) return rc; }
     int n2 = 0;
     for (int k = 0; k < d.n_stages; ++k) n2 += d.stages[k].n;
