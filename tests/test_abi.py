@@ -30,14 +30,25 @@ def test_ctypes_binding_covers_the_header(built_lib):
 
 
 def test_struct_layouts_match_the_header(built_lib):
-    """sizeof() of the ctypes mirrors equals what the C compiler lays out."""
+    """sizeof() AND every field offset of the ctypes mirrors equal what the C compiler lays out."""
     import subprocess
     import tempfile
     from iactrace_b200 import _native as N
-    src = '#include <stdio.h>\n#include "iactrace_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",sizeof(IactSurface),sizeof(IactMirrorStage),sizeof(IactSensor),sizeof(IactScene),sizeof(IactFacets),sizeof(IactGrads));return 0;}\n'
+    structs = (N.IactSurface, N.IactMirrorStage, N.IactSensor, N.IactScene, N.IactFacets, N.IactGrads)
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "iactrace_b200.h"', 'int main(){']
+    for c in structs:
+        lines.append(f'printf("{c.__name__} %zu", sizeof({c.__name__}));')
+        for name, *_ in c._fields_:
+            lines.append(f'printf(" %zu", offsetof({c.__name__}, {name}));')
+        lines.append('printf("\\n");')
+    lines.append('return 0;}')
     with tempfile.TemporaryDirectory() as d:
-        (Path(d) / "s.c").write_text(src)
+        (Path(d) / "s.c").write_text("\n".join(lines))
         subprocess.run(["gcc", "-I", str(ROOT / "include"), str(Path(d) / "s.c"), "-o", str(Path(d) / "s")], check=True)
-        out = subprocess.run([str(Path(d) / "s")], capture_output=True, text=True, check=True).stdout.split()
-    want = [ctypes.sizeof(c) for c in (N.IactSurface, N.IactMirrorStage, N.IactSensor, N.IactScene, N.IactFacets, N.IactGrads)]
-    assert [int(x) for x in out] == want
+        out = subprocess.run([str(Path(d) / "s")], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    assert len(out) == len(structs)
+    for c, line in zip(structs, out):
+        got = line.split()
+        assert got[0] == c.__name__
+        want = [ctypes.sizeof(c)] + [getattr(c, name).offset for name, *_ in c._fields_]
+        assert [int(x) for x in got[1:]] == want, c.__name__

@@ -84,3 +84,36 @@ def test_gradient_through_sample_windows():
             torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5 * float(b.abs().max()))
     finally:
         Rm.window_table_bytes = old
+
+
+def test_window_rays_are_bit_identical_to_the_table_path():
+    """Per ray: the rays traced from a regenerated sample window are bit-identical to the same rows of the render_debug
+    output of the fully materialised draw (the windows are what `render` sums when the samples are streamed)."""
+    from iactrace_b200.core.streaming import window_plan, iter_windows
+    cfg = subset_config(load_packed_config("CT5"), mirror_step=25)
+    src = point_grid(2, 1.5)
+    val = np.linspace(0.5, 1.5, len(src)).astype(np.float32)
+    M = 700
+    held = build_telescope(cfg, MCIntegrator(M, stream=False), R.key(11))
+    streamed = build_telescope(cfg, MCIntegrator(M, stream=True), R.key(11))
+    F, S = len(held.mirror_groups[0]), len(src)
+    old = Rm.window_table_bytes
+    try:
+        Rm.window_table_bytes = 1 << 40
+        xy, v, pix = render_debug(held, src, val, "point", 0, return_pixels=True)
+        xy, v, pix = xy.reshape(F, S, M, 2), v.reshape(F, S, M), pix.reshape(F, S, M)
+        Rm.window_table_bytes = F * 32 * 260                                  # windows of 256 samples
+        plan = window_plan(streamed)
+        assert len(plan) == 3
+        seen = 0
+        for (first, n), tw in zip(plan, iter_windows(streamed, plan)):
+            Rm.window_table_bytes = 1 << 40                                   # the window itself is traced in one go
+            wxy, wv, wpix = render_debug(tw, src, val, "point", 0, return_pixels=True)
+            Rm.window_table_bytes = F * 32 * 260
+            assert torch.equal(wxy.reshape(F, S, n, 2), xy[:, :, first:first + n])
+            assert torch.equal(wv.reshape(F, S, n), v[:, :, first:first + n])
+            assert torch.equal(wpix.reshape(F, S, n), pix[:, :, first:first + n])
+            seen += n
+        assert seen == M and float((v != 0).float().mean()) > 0.5
+    finally:
+        Rm.window_table_bytes = old
