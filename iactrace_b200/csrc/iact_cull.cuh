@@ -135,6 +135,64 @@ __device__ __forceinline__ int build_list(const ObsSmem& ob, const Beam& b, cons
     return n;
 }
 
+// Level-2 list AND cylinder records of an item whose rays share the unit direction -u (far point / parallel sources)
+// in one pass: lane e takes level-1 candidate e (n_cand <= 32, cylinders first), evaluates the direction half of the
+// cylinder test (cyl_dir), which the record needs anyway, and runs the capsule test of beam_keeps_capsule on top of it:
+// with p2 = p1 + h ax the segment in the plane normal to u is q1 + s h (ax - (ax.u) u), of squared length h^2 a.  Same
+// margins as beam_keeps_capsule (the axis of the staged table differs from (p2 - p1) / h by float32 rounding, ~1e-7 h,
+// against 2 mm).  Kept cylinders write their record at their compacted position; other primitives go through the
+// proxy test.  Returns the list length, sets n_cyl_out; records beyond CYL_REC_MAX are not written (the ray loop
+// finishes those inline).
+__device__ __forceinline__ int build_list_uni(const ObsSmem& ob, const Beam& b, const unsigned short* __restrict__ cand, int n_cand_cyl,
+                                              int n_cand, unsigned short* out, float* wrec, int& n_cyl_out) {
+    const unsigned lane = threadIdx.x & 31u;
+    bool keep = false;
+    int id = 0;
+    CylDir cd;
+    const float* c = nullptr;
+    if ((int)lane < n_cand) {
+        id = (int)cand[lane];
+        if ((int)lane < n_cand_cyl) {
+            c = ob.cyl + CYL_STRIDE * id;
+            const V3 p1 = v3(c[0], c[1], c[2]), ax = v3(c[3], c[4], c[5]);
+            const float h = c[6], r = fabsf(c[7]) * 1.0001f;
+            cd = cyl_dir(ax, b.u);
+            const V3 a1 = p1 - b.c;
+            const float t1 = dot(a1, b.u), t2 = t1 + h * cd.rd_ax;
+            const float tmx = fmaxf(t1, t2);
+            const float marg = 2e-3f;
+            if (!(tmx + r < -(b.R + marg))) {                       // else: wholly behind every ray origin
+                const float tmax = 1.1f * (fmaxf(tmx, 0.f) + r + b.R);
+                const float Reff = b.R * (1.0f + 1.5708f * tmax * b.invD) + marg + 1e-5f * tmax;
+                const V3 q1 = a1 - t1 * b.u;
+                const V3 e = h * (ax - cd.rd_ax * b.u);
+                const float ee = h * h * cd.a;
+                const float sp = ee > 1e-20f ? fminf(fmaxf(-dot(q1, e) * frcp_fast(ee), 0.f), 1.f) : 0.f;
+                const V3 dv = q1 + sp * e;
+                const float lim = Reff + r;
+                keep = dot(dv, dv) <= lim * lim;
+            }
+        } else {
+            keep = keep_primitive(ob, b, id);
+        }
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, keep);
+    const int pos = __popc(mask & ((1u << lane) - 1u));
+    if (keep) {
+        out[pos] = (unsigned short)id;
+        if (c && pos < CYL_REC_MAX) {
+            float4* q = reinterpret_cast<float4*>(wrec + CYL_REC * pos);
+            q[0] = make_float4(c[0], c[1], c[2], c[6]);
+            q[1] = make_float4(c[3], c[4], c[5], __fmul_rn(c[7], c[7]));
+            q[2] = make_float4(cd.rdp2.x, cd.rdp2.y, cd.rdp2.z, cd.rd_ax);
+            q[3] = make_float4(cd.a4, cd.inv2a, cd.inv_ax, cd.a);
+        }
+    }
+    n_cyl_out = n_cand_cyl >= 32 ? __popc(mask) : __popc(mask & ((1u << n_cand_cyl) - 1u));
+    __syncwarp();
+    return __popc(mask);
+}
+
 // _check_occlusions for the leg towards an optical stage >= 1 (render.py:76), culled per warp from the
 // rays themselves: origins lie within R of the leader lane's origin and directions within `spread`
 // (chord) of the leader's, so a primitive that beam cannot reach is skipped for all 32 rays.  Exact for

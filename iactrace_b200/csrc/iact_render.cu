@@ -304,6 +304,9 @@ struct PixCache {
 #ifndef IACT_HEX_FAST2
 #define IACT_HEX_FAST2 1     // second fast path (slot 1's hexagon) + rays outside the camera's bounding circle
 #endif
+#ifndef IACT_UNI_LIST
+#define IACT_UNI_LIST 1      // level-2 list and cylinder records of a shared-direction item in one pass
+#endif
 #ifndef IACT_FAR_UNIFORM
 #define IACT_FAR_UNIFORM 1   // one direction per (facet, source) item for point sources with parallax R / D < 1e-9
 #endif
@@ -468,32 +471,47 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
                                            float* __restrict__ out_val, int* __restrict__ out_pix) {
     const int lane = threadIdx.x & 31;
     const int M = sc.M;
-    int n_list = 0, n_list_cyl = 0;
+    int n_list = 0, n_list_cyl = 0, n_rec = 0;
     Beam beam;
     beam.ok = false;
-    if (cx.cull) {
-        beam = make_beam<SRC>(__ldg(sc.bounds + f), src);
-        n_list = item_list(cx, fl, beam, f, n_list_cyl);
-    }
     // Rays of one item that share their direction: parallel sources, and point sources so far away that the parallax
     // across the facet (R / D < 1e-9) is below what float32 resolves in `normalize(p - src)` (render.py:130-131: the
     // subtraction itself rounds p away at that distance).  The direction is then evaluated once, from the facet
     // centre, and the direction half of the cylinder tests once per (item, candidate) into the warp's records.
     bool uni = SRC != IACT_SOURCE_POINT;
     V3 sd = src;
-    if (SRC == IACT_SOURCE_POINT && IACT_FAR_UNIFORM) {
-        const float4 bnd = __ldg(sc.bounds + f);
-        const V3 ac = sub_rn(v3(bnd.x, bnd.y, bnd.z), src);
-        const float n2 = dot_rn(ac, ac);
-        if (bnd.w * bnd.w < 1e-18f * n2 && n2 < 1e37f) { uni = true; sd = scale_rn(frsqrt_nr_rn(n2), ac); }
+    float unit_dev = 0.f;                                            // | |u|^2 - 1 | of the shared direction
+    const float4 bnd = __ldg(sc.bounds + f);
+    if (SRC == IACT_SOURCE_POINT) {
+        if (IACT_FAR_UNIFORM) {
+            const V3 ac = sub_rn(v3(bnd.x, bnd.y, bnd.z), src);
+            const float n2 = dot_rn(ac, ac);
+            if (bnd.w * bnd.w < 1e-18f * n2 && n2 < 1e37f) { uni = true; sd = scale_rn(frsqrt_nr_rn(n2), ac); }
+        }
+    } else {
+        unit_dev = fabsf(dot_rn(src, src) - 1.0f);                    // parallel directions are not normalised by the library
     }
     // records pay from three 32-ray iterations per item on (CT3 response matrix at M = 64: 1.125 -> 1.10 ms without) and
     // not in the stage >= 1 kernels, which are short of registers (Cassegrain: 32.4 -> 31.1 ms without)
-    int n_rec = 0;
-    if (IACT_CYL_RECORDS && !STAGES && uni && cx.wrec && m1 - m0 > 64) {
-        n_rec = min(n_list_cyl, CYL_REC_MAX);
-        if (lane < n_rec) cyl_record_write(cx.wrec + CYL_REC * lane, cx.ob.cyl + CYL_STRIDE * cx.list[lane], -sd);
-        __syncwarp();
+    const bool want_rec = IACT_CYL_RECORDS && !STAGES && uni && cx.wrec && m1 - m0 > 64;
+    if (cx.cull) {
+        const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
+        if (IACT_UNI_LIST && want_rec && cnt.x >= 0 && cnt.y <= 32 && unit_dev < 1e-4f) {
+            // list and records in one pass (iact_cull.cuh build_list_uni); the beam axis is the shared direction itself
+            beam.c = v3(bnd.x, bnd.y, bnd.z); beam.R = bnd.w; beam.spread = 0.f; beam.u = -sd; beam.ok = true;
+            beam.invD = 0.f;
+            if (SRC == IACT_SOURCE_POINT) { const V3 ac = sub_rn(beam.c, src); beam.invD = frsqrt_fast(dot_rn(ac, ac)); }
+            n_list = build_list_uni(cx.ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, cx.list, cx.wrec, n_list_cyl);
+            n_rec = min(n_list_cyl, CYL_REC_MAX);
+        } else {
+            beam = make_beam<SRC>(bnd, src);
+            n_list = item_list(cx, fl, beam, f, n_list_cyl);
+            if (want_rec) {
+                n_rec = min(n_list_cyl, CYL_REC_MAX);
+                if (lane < n_rec) cyl_record_write(cx.wrec + CYL_REC * lane, cx.ob.cyl + CYL_STRIDE * cx.list[lane], -sd);
+                __syncwarp();
+            }
+        }
     }
     const float4* tab = sc.world + ((size_t)f * M) * 2;
     SoftHexCache scache;
