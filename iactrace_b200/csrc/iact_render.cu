@@ -315,8 +315,9 @@ struct PixCache {
 #define IACT_MIN_BLOCKS 4
 #endif
 #ifndef IACT_MIN_BLOCKS_RENDER_HEX
-#define IACT_MIN_BLOCKS_RENDER_HEX 5 // render on a hard hex camera without level-3 culling: five resident blocks at 51 registers
-#endif                               // (a few dozen bytes of spills) beat four at 62 by 2 %; the other instantiations lose 0-6 %
+#define IACT_MIN_BLOCKS_RENDER_HEX 5 // render on a hard hex camera: five resident blocks at 48 registers (a few dozen bytes of
+#endif                               // spills) beat four at 62 by 2-4 % (r2: also with level-3 culling, M = 4096: 87.3 -> 83.5 ms);
+                                     // square cameras and the response matrix lose 2-20 % at five (spills) and stay at four
 #ifndef IACT_MIN_BLOCKS_STAGES
 #define IACT_MIN_BLOCKS_STAGES 3
 #endif
@@ -480,23 +481,20 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
     // centre, and the direction half of the cylinder tests once per (item, candidate) into the warp's records.
     bool uni = SRC != IACT_SOURCE_POINT;
     V3 sd = src;
-    float unit_dev = 0.f;                                            // | |u|^2 - 1 | of the shared direction
     const float4 bnd = __ldg(sc.bounds + f);
-    if (SRC == IACT_SOURCE_POINT) {
-        if (IACT_FAR_UNIFORM) {
-            const V3 ac = sub_rn(v3(bnd.x, bnd.y, bnd.z), src);
-            const float n2 = dot_rn(ac, ac);
-            if (bnd.w * bnd.w < 1e-18f * n2 && n2 < 1e37f) { uni = true; sd = scale_rn(frsqrt_nr_rn(n2), ac); }
-        }
-    } else {
-        unit_dev = fabsf(dot_rn(src, src) - 1.0f);                    // parallel directions are not normalised by the library
+    if (SRC == IACT_SOURCE_POINT && IACT_FAR_UNIFORM) {
+        const V3 ac = sub_rn(v3(bnd.x, bnd.y, bnd.z), src);
+        const float n2 = dot_rn(ac, ac);
+        if (bnd.w * bnd.w < 1e-18f * n2 && n2 < 1e37f) { uni = true; sd = scale_rn(frsqrt_nr_rn(n2), ac); }
     }
     // records pay from three 32-ray iterations per item on (CT3 response matrix at M = 64: 1.125 -> 1.10 ms without) and
     // not in the stage >= 1 kernels, which are short of registers (Cassegrain: 32.4 -> 31.1 ms without)
     const bool want_rec = IACT_CYL_RECORDS && !STAGES && uni && cx.wrec && m1 - m0 > 64;
     if (cx.cull) {
         const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
-        if (IACT_UNI_LIST && want_rec && cnt.x >= 0 && cnt.y <= 32 && unit_dev < 1e-4f) {
+        // (parallel directions are not normalised by the library: the one-pass form needs a unit direction)
+        if (IACT_UNI_LIST && want_rec && cnt.x >= 0 && cnt.y <= 32 &&
+            (SRC == IACT_SOURCE_POINT || fabsf(dot_rn(src, src) - 1.0f) < 1e-4f)) {
             // list and records in one pass (iact_cull.cuh build_list_uni); the beam axis is the shared direction itself
             beam.c = v3(bnd.x, bnd.y, bnd.z); beam.R = bnd.w; beam.spread = 0.f; beam.u = -sd; beam.ok = true;
             beam.invD = 0.f;
@@ -559,7 +557,7 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
 // pulled from the same counter (queue.counter == nullptr there selects a static grid-stride split).
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
 __global__ void __launch_bounds__(256, STAGES ? IACT_MIN_BLOCKS_STAGES
-                                              : ((MODE == MODE_RENDER && SENS == SENS_HEX && !SUB) ? IACT_MIN_BLOCKS_RENDER_HEX
+                                              : ((MODE == MODE_RENDER && SENS == SENS_HEX) ? IACT_MIN_BLOCKS_RENDER_HEX
                                                  : (SENS == SENS_SOFT_HEX ? IACT_MIN_BLOCKS_SOFT : IACT_MIN_BLOCKS)))
 trace_kernel(const __grid_constant__ SceneDev sc, const float* __restrict__ sources, const float* __restrict__ values,
              const LaunchPlan plan, const QueuePlan queue, const FacetLists fl, float* __restrict__ out,
