@@ -343,9 +343,16 @@ __global__ void __launch_bounds__(256, STAGES ? IACT_VJP_MIN_BLOCKS_STAGES : (FU
 vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float* __restrict__ sources,
            const float* __restrict__ values, const VjpPlan vp, const FacetLists fl,
            const float* __restrict__ G, const GradsDev gr) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(16) float smem_all[];
+    float* smem = smem_all;
     ObsSmem ob;
     const bool cull = sc.cull != 0;
+    // per-warp cylinder records (as trace_kernel): items whose rays share their direction
+    float* wrec = nullptr;
+    if (IACT_CYL_RECORDS && cull && sc.n_cyl > 0) {
+        wrec = smem + (size_t)(threadIdx.x >> 5) * (CYL_REC_MAX * CYL_REC);
+        smem += (size_t)(blockDim.x >> 5) * (CYL_REC_MAX * CYL_REC);
+    }
     stage_obstructions(sc, smem, ob, cull);
     const int n_obs = ob.n_cyl + ob.n_rest;
     float* p = smem + obstruction_floats(sc.n_cyl, sc.n_box, sc.n_sph, sc.n_obox, sc.n_tri, cull);
@@ -405,22 +412,31 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
             const float sval = __ldg(values + s);
             float g_val = 0.f;
             V3 g_src = v3(0.f, 0.f, 0.f);
-            int n_list = 0, n_list_cyl = 0;
-            if (cull) {
-                const Beam beam = make_beam<SRC>(bnd, src);
-                const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
-                if (cnt.x >= 0) n_list = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, n_list_cyl);
-                else            n_list = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, n_list_cyl);
-            }
-
             // far point source (parallax R / D < 1e-9, as trace_item): one direction for the whole facet, and the
             // adjoint of that direction w.r.t. the ray origin (~1/D) is dropped -- unless d/d(sources) was asked for
-            bool uni = false;
+            bool uni = SRC != IACT_SOURCE_POINT;
             V3 sd = src;
             if (SRC == IACT_SOURCE_POINT && !(FULL && gr.sources)) {
                 const V3 ac = sub_rn(v3(bnd.x, bnd.y, bnd.z), src);
                 const float n2 = dot_rn(ac, ac);
                 if (bnd.w * bnd.w < 1e-18f * n2 && n2 < 1e37f) { uni = true; sd = scale_rn(frsqrt_nr_rn(n2), ac); }
+            }
+            int n_list = 0, n_list_cyl = 0, n_rec = 0;
+            if (cull) {
+                const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
+                if (wrec && uni && m1 - m0 > 64 && cnt.x >= 0 && cnt.y <= 32 &&
+                    (SRC == IACT_SOURCE_POINT || fabsf(dot_rn(src, src) - 1.0f) < 1e-4f)) {
+                    Beam beam;                                   // list and records in one pass (build_list_uni)
+                    beam.c = v3(bnd.x, bnd.y, bnd.z); beam.R = bnd.w; beam.spread = 0.f; beam.u = -sd; beam.ok = true;
+                    beam.invD = 0.f;
+                    if (SRC == IACT_SOURCE_POINT) { const V3 ac = sub_rn(beam.c, src); beam.invD = frsqrt_fast(dot_rn(ac, ac)); }
+                    n_list = build_list_uni(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, wrec, n_list_cyl);
+                    n_rec = min(n_list_cyl, CYL_REC_MAX);
+                } else {
+                    const Beam beam = make_beam<SRC>(bnd, src);
+                    if (cnt.x >= 0) n_list = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, n_list_cyl);
+                    else            n_list = build_list(ob, beam, (const unsigned short*)nullptr, ob.n_cyl, n_obs, list, n_list_cyl);
+                }
             }
 
             for (int m = m0 + lane; m < m1; m += 32) {
@@ -444,7 +460,7 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                 }
                 V3 d = sd; float inv_a = 0.f;
                 if (SRC == IACT_SOURCE_POINT && !uni) { d = o - src; inv_a = frsqrt_nr(dot(d, d)); d = inv_a * d; }
-                if (occluded(ob, o, -d, list, n_list_cyl, n_list)) continue;
+                if (occluded(ob, o, -d, list, n_list_cyl, n_list, 0xffffffffu, wrec, n_rec)) continue;
                 const float c = dot(d, n);
                 const V3 r = d - (2.0f * c) * n;
                 const float val0 = (sval * (-c)) * inv_w;
@@ -722,6 +738,7 @@ extern "C" int iact_render_vjp(const IactScene* scene, const IactFacets* facets,
     if (hex) smem += (size_t)((d.sens.tq * d.sens.tr + 1) / 2) * 4;
     smem += (size_t)stage_floats(d) * 4;
     if (d.cull) smem += (size_t)(threads / 32) * ((d.n_cyl + d.n_box + d.n_sph + d.n_obox + d.n_tri + 1) & ~1) * 2;
+    if (IACT_CYL_RECORDS && d.cull && d.n_cyl > 0) smem += (size_t)(threads / 32) * CYL_REC_MAX * CYL_REC * 4;
     if (smem > 200 * 1024) { iact_set_error("scene needs %zu bytes of shared memory per block (limit 204800)", smem); return IACT_ERR_UNSUPPORTED; }
     auto launch = [&](auto kern) -> int {
         if (smem > 48 * 1024) IACT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
