@@ -87,3 +87,33 @@ def test_two_gpu_sharded_render_matches_single_gpu():
         for got, w in zip((g_rot, g_scale, g_val), want_g):
             np.testing.assert_allclose(got, w, rtol=1e-4, atol=2e-5 * np.abs(w).max())
     assert (res[0][4], res[0][5], res[1][4], res[1][5]) == (0, 25, 25, 49)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_render_follows_the_telescope_device():
+    """Multi-GPU in ONE process: the kernels dereference the telescope's tensors, so inputs, outputs and the launch
+    follow the device the telescope lives on, whatever the current device is (core/render.py::scene_device)."""
+    import iactrace_b200 as I
+    from iactrace_b200.core import render
+    from iactrace_b200.io import build_telescope, load_packed_config
+    from iactrace_b200.workloads import point_grid
+    cfg = load_packed_config("CT3")
+    cfg = dict(cfg, mirrors=cfg["mirrors"][::12])
+    src, val = point_grid(3, 1.0), np.ones(9, np.float32)
+    torch.cuda.set_device(0)
+    tel0 = build_telescope(cfg, I.MCIntegrator(16), I.random.key(0))
+    want = render(tel0, src, val, "point", 0)
+    with torch.cuda.device(1):
+        tel1 = build_telescope(cfg, I.MCIntegrator(16), I.random.key(0))
+    assert tel1.mirror_groups[0].points.device.index == 1
+    assert torch.cuda.current_device() == 0
+    got = render(tel1, src, val, "point", 0)                       # current device 0, telescope on device 1
+    assert got.device.index == 1
+    torch.testing.assert_close(got.cpu(), want.cpu(), rtol=2e-5, atol=1e-7)
+    got2 = render(tel1, torch.from_numpy(src).cuda(0), val, "point", 0)    # sources on the other device are moved
+    torch.testing.assert_close(got2.cpu(), want.cpu(), rtol=2e-5, atol=1e-7)
+    # a telescope spread over two devices is refused with a clear error
+    from iactrace_b200._util import replace
+    bad = replace(tel1, sensors=tel0.sensors)
+    with pytest.raises(ValueError, match="several devices"):
+        render(bad, src, val, "point", 0)
