@@ -19,6 +19,7 @@ MAX_ASPH = 8
 MAX_STAGES = 4
 MAX_POLY = 16
 MIRROR_REC = 24
+RUN_BOUND_FLOATS = 8    # IACT_RUN_BOUND_FLOATS: floats per 32-row run of IactScene.chunk_bounds
 
 RNG_PARTITIONABLE = 0
 RNG_LEGACY = 1

@@ -123,7 +123,7 @@ class _Render(torch.autograd.Function):
                 sub.world = sc.world + off * M * 8 * 4
                 sub.bounds = sc.bounds + off * 4 * 4
                 if sc.chunk_bounds:
-                    sub.chunk_bounds = sc.chunk_bounds + off * ((M + 31) // 32) * 4 * 4
+                    sub.chunk_bounds = sc.chunk_bounds + off * ((M + 31) // 32) * N.RUN_BOUND_FLOATS * 4
                 gr_struct = N.IactGrads(N.ptr(gp), N.ptr(gr), N.ptr(gs), N.ptr(gw), N.ptr(g_val), N.ptr(g_src),
                                         N.ptr(g_spos), N.ptr(g_srot), N.ptr(g_mpos), N.ptr(g_mrot),
                                         N.ptr(gpts), N.ptr(gnq), N.ptr(g_msurf))

@@ -52,7 +52,7 @@ def _world_tables(tel, stage0, later_stages=False):
     dev = stage0[0].points.device
     world = torch.empty((F, M, 8), dtype=torch.float32, device=dev)
     bounds = torch.empty((F, 4), dtype=torch.float32, device=dev)
-    chunks = torch.empty((F, (M + 31) // 32, 4), dtype=torch.float32, device=dev) if binned else None
+    chunks = torch.empty((F, (M + 31) // 32, N.RUN_BOUND_FLOATS), dtype=torch.float32, device=dev) if binned else None
     grid_side = max(1, min(16, int(round(math.sqrt(M / 32.0)))))
     off = 0
     for g in stage0:

@@ -97,7 +97,7 @@ __device__ __forceinline__ unsigned strip_masks(const ObsSmem& ob, const Beam& b
             srr = r + 2e-3f + 1e-5f * tfar + beam.R * 1.5708f * tfar * beam.invD;
         }
     }
-    const float4 cb = __ldg(cbs + min(run0 + lane, n_runs - 1));
+    const float4 cb = __ldg(cbs + 2 * min(run0 + lane, n_runs - 1));
     unsigned mask = 0u;
     for (int e = 0; e < n_list; ++e) {
         const float nx = __shfl_sync(0xffffffffu, sn.x, e), ny = __shfl_sync(0xffffffffu, sn.y, e), nz = __shfl_sync(0xffffffffu, sn.z, e);
@@ -232,6 +232,51 @@ __device__ __forceinline__ bool occluded_leg_culled(const ObsSmem& ob, V3 o, V3 
         }
     }
     return blocked;
+}
+
+// The same leg culled per 32-row RUN of a binned table instead of per iteration from the rays (first optical stage
+// >= 1 only, at most 32 primitives): lane j bounds the reflected rays of run run0 + j without tracing them.  The rows
+// of a run start within R of c (bounding sphere) and their normals lie within e of the unit mean normal nb (normal
+// cone, transform_binned_kernel).  With the incoming direction d (shared by the item, or towards a point source:
+// then it varies by at most dd = 1.5708 R / D over the run), the reflected direction r(d, n) = d - 2 (d.n) n obeys
+//   |r(d, n) - r(d0, nb)| <= |I - 2 n n^T| |d - d0| + 2 |d0| |n - nb| (2 |nb| + |n - nb|)
+//                         <= dd (1 + 2 (|nb| + e)^2) + 2 |d0| e (2 |nb| + e),
+// which is the `spread` of a Beam about u = r(d0, nb): the same conservative capsule test as everywhere else then
+// yields, per run, the mask (bit p = primitive p) of what the leg can reach.  About 60 instructions per primitive for
+// 32 runs, against about 150 per iteration for the dynamic version.  A degenerate run keeps everything.
+template <int SRC>
+__device__ __forceinline__ unsigned leg_masks(const ObsSmem& ob, V3 src, bool uni, V3 sd, const float4* __restrict__ cbs,
+                                              int n_runs, int run0) {
+    const int lane = threadIdx.x & 31;
+    const int run = min(run0 + lane, n_runs - 1);
+    const float4 cb = __ldg(cbs + 2 * run), cn = __ldg(cbs + 2 * run + 1);
+    Beam b;
+    b.c = v3(cb.x, cb.y, cb.z); b.R = cb.w; b.invD = 0.f;
+    V3 d = sd;
+    float dd = 0.f;
+    bool ok = true;
+    if (SRC == IACT_SOURCE_POINT && !uni) {
+        const V3 a = b.c - src;
+        const float n2 = dot(a, a);
+        ok = n2 > 1e-30f && n2 < 1e37f;
+        const float inv = rsqrtf(ok ? n2 : 1.f);
+        d = inv * a;
+        dd = 1.5708f * b.R * inv * 1.001f;
+        ok = ok && b.R * inv < 0.1f;
+    }
+    const V3 nb = v3(cn.x, cn.y, cn.z);
+    const float e = cn.w, dl = sqrtf(dot(d, d)), nl = sqrtf(dot(nb, nb)), nmax = nl + e;
+    b.u = d - (2.0f * dot(d, nb)) * nb;
+    b.spread = (dd * (1.0f + 2.0f * nmax * nmax) + 2.0f * dl * e * (2.0f * nl + e)) * 1.001f + 1e-6f;
+    const float u2 = dot(b.u, b.u);
+    ok = ok && (b.spread < 0.15f) && (b.R < 1e6f) && (u2 > 0.99f) && (u2 < 1.01f);
+    const int n_obs = ob.n_cyl + ob.n_rest;
+    if (!ok) return n_obs >= 32 ? 0xffffffffu : (1u << n_obs) - 1u;
+    b.ok = true;
+    unsigned mask = 0u;
+    for (int p = 0; p < n_obs; ++p)
+        if (keep_primitive(ob, b, p)) mask |= 1u << p;
+    return mask;
 }
 
 // ---------------------------------------------------------------- level-1 culling: facet x all sources

@@ -307,6 +307,9 @@ struct PixCache {
 #ifndef IACT_UNI_LIST
 #define IACT_UNI_LIST 1      // level-2 list and cylinder records of a shared-direction item in one pass
 #endif
+#ifndef IACT_LEG_MASKS
+#define IACT_LEG_MASKS 1     // leg towards optical stage 1 culled per 32-row run of a binned table (not per iteration)
+#endif
 #ifndef IACT_FAR_UNIFORM
 #define IACT_FAR_UNIFORM 1   // one direction per (facet, source) item for point sources with parallax R / D < 1e-9
 #endif
@@ -373,8 +376,8 @@ __device__ __forceinline__ void trace_setup(const SceneDev& sc, float* smem, Tra
 // entries then have a CylRec record.  Called by all 32 lanes; `live` = this lane holds a real ray.
 template <int SRC, int SENS, int MODE, bool STAGES, bool SUB>
 __device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx, float4 a, float4 b, V3 sd, bool uni, float sval, bool live,
-                                          int n_list_cyl, int n_list, int n_rec, unsigned sub_mask, size_t ri, bool soft7,
-                                          PixCache& cache, SoftHexCache& scache, float* __restrict__ gout,
+                                          int n_list_cyl, int n_list, int n_rec, unsigned sub_mask, bool leg_static, unsigned leg_mask,
+                                          size_t ri, bool soft7, PixCache& cache, SoftHexCache& scache, float* __restrict__ gout,
                                           float* __restrict__ out_val, int* __restrict__ out_pix) {
     const ObsSmem& ob = cx.ob;
     V3 o = v3(a.x, a.y, a.z);
@@ -394,8 +397,15 @@ __device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx
     if (STAGES) {
         const float* rec = cx.stage_rec;
         for (int st = 0; st < sc.n_stages; ++st) {
-            const bool leg_blocked = cx.cull ? occluded_leg_culled(ob, o, d, val != 0.f)
-                                             : occluded(ob, o, d, nullptr, 0, 0);
+            bool leg_blocked = false;
+            if (!cx.cull) leg_blocked = occluded(ob, o, d, nullptr, 0, 0);
+            else if (SUB && leg_static && st == 0) {               // per-run mask of reachable primitives (leg_masks)
+                const bool need = val != 0.f;
+                for (unsigned mk = leg_mask; mk; mk &= mk - 1u) {
+                    const int p = __ffs(mk) - 1;
+                    if (need) leg_blocked |= hit_primitive(ob, p, o, d);
+                }
+            } else leg_blocked = occluded_leg_culled(ob, o, d, val != 0.f);
             reflect_at_stage(sc.stages[st].n, rec, sc.stages[st].verts, leg_blocked, !cx.cull, o, d, val);
             rec += (size_t)sc.stages[st].n * STAGE_REC;
         }
@@ -517,16 +527,23 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
     if (soft7) scache.reset();
     // level-3 culling: with a binned table every run of 32 rows is a compact patch of the facet
     const bool sub_beams = SUB && cx.cull && n_list >= 1 && n_list <= 32;
-    const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) : nullptr;
+    const float4* cbs = sub_beams ? sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) * 2 : nullptr;
     // far or parallel sources: strip test, the masks of 32 consecutive runs at once (iact_cull.cuh strip_masks), so
     // nothing but one mask word per lane stays live across the ray loop; nearer sources: capsule test per run
     const bool strip = SUB && sub_beams && strip_applies(beam);
     auto run_strip_masks = [&](int run0) -> unsigned {
         const Beam b = make_beam<SRC>(__ldg(sc.bounds + f), src);           // recomputed: nothing of it stays live in the ray loop
-        return strip_masks(cx.ob, b, cx.list, n_list_cyl, n_list, sc.chunk_bounds + (size_t)f * ((M + 31) >> 5), (M + 31) >> 5, run0);
+        return strip_masks(cx.ob, b, cx.list, n_list_cyl, n_list, sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) * 2, (M + 31) >> 5, run0);
     };
     unsigned run_masks = 0xffffffffu;                                        // lane j: run ((mb >> 5) & ~31) + j
     if (SUB && strip) run_masks = run_strip_masks((m0 >> 5) & ~31);
+    // the leg towards the first optical stage >= 1, culled per run as well (iact_cull.cuh leg_masks)
+    const bool leg_static = IACT_LEG_MASKS && STAGES && SUB && cx.cull && sc.n_stages > 0 && cx.ob.n_cyl + cx.ob.n_rest <= 32;
+    auto run_leg_masks = [&](int run0) -> unsigned {
+        return leg_masks<SRC>(cx.ob, src, uni, sd, sc.chunk_bounds + (size_t)f * ((M + 31) >> 5) * 2, (M + 31) >> 5, run0);
+    };
+    unsigned leg_run_masks = 0xffffffffu;
+    if (STAGES && SUB && leg_static) leg_run_masks = run_leg_masks((m0 >> 5) & ~31);
     for (int mb = m0; mb < m1; mb += 32) {
         const int m = mb + lane;
         const bool live = m < m1;
@@ -538,13 +555,18 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
                 if (((mb >> 5) & 31) == 0 && mb != m0) run_masks = run_strip_masks(mb >> 5);
                 sub_mask = __shfl_sync(0xffffffffu, run_masks, (mb >> 5) & 31);
             } else {
-                const Beam cb = make_beam<SRC>(__ldg(cbs + (mb >> 5)), src);
+                const Beam cb = make_beam<SRC>(__ldg(cbs + 2 * (mb >> 5)), src);
                 sub_mask = __ballot_sync(0xffffffffu, lane < n_list && (!cb.ok || keep_primitive(cx.ob, cb, cx.list[lane])));
             }
         }
+        unsigned leg_mask = 0xffffffffu;
+        if (STAGES && SUB && leg_static) {
+            if (((mb >> 5) & 31) == 0 && mb != m0) leg_run_masks = run_leg_masks(mb >> 5);
+            leg_mask = __shfl_sync(0xffffffffu, leg_run_masks, (mb >> 5) & 31);
+        }
         const size_t ri = ((size_t)f * S + s) * M + __float_as_int(b.w);   // debug: original sample index
-        trace_ray<SRC, SENS, MODE, STAGES, SUB>(sc, cx, a, b, sd, uni, sval, live, n_list_cyl, n_list, n_rec, sub_mask, ri, soft7,
-                                                cache, scache, gout, out_val, out_pix);
+        trace_ray<SRC, SENS, MODE, STAGES, SUB>(sc, cx, a, b, sd, uni, sval, live, n_list_cyl, n_list, n_rec, sub_mask, leg_static,
+                                                leg_mask, ri, soft7, cache, scache, gout, out_val, out_pix);
     }
     if (SENS == SENS_SOFT_HEX && soft7) scache.flush(sc.sens, cx.lut, cx.hist);
     __syncwarp();
@@ -677,10 +699,10 @@ __global__ void __launch_bounds__(256) cull_stats_kernel(const __grid_constant__
             for (int k = 0; k < n_chunks; ++k) {
                 unsigned mask;
                 if (strip) {
-                    if ((k & 31) == 0) masks = strip_masks(ob, beam, list, ncyl, n, sc.chunk_bounds + (size_t)f * n_chunks, n_chunks, k);
+                    if ((k & 31) == 0) masks = strip_masks(ob, beam, list, ncyl, n, sc.chunk_bounds + (size_t)f * n_chunks * 2, n_chunks, k);
                     mask = __shfl_sync(0xffffffffu, masks, k & 31);
                 } else {
-                    const Beam cb = make_beam<SRC>(__ldg(sc.chunk_bounds + (size_t)f * n_chunks + k), src);
+                    const Beam cb = make_beam<SRC>(__ldg(sc.chunk_bounds + ((size_t)f * n_chunks + k) * 2), src);
                     mask = __ballot_sync(0xffffffffu, lane < n && (!cb.ok || keep_primitive(ob, cb, list[lane])));
                 }
                 const unsigned mc = ncyl >= 32 ? mask : (mask & ((1u << ncyl) - 1u));

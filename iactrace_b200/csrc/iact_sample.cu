@@ -221,11 +221,13 @@ __global__ void __launch_bounds__(256) transform_binned_kernel(const IactFacets 
         b[0] = pos.x; b[1] = pos.y; b[2] = pos.z;
         b[3] = sqrtf(red[0][0]) * 1.00001f + 1e-6f;
     }
-    // bounding sphere of every run of 32 rows: centre = bounding-box centre, radius = farthest row
+    // per run of 32 rows: bounding sphere (centre = bounding-box centre, radius = farthest row) and normal cone
+    // (unit mean normal, largest distance of a row's normal from it: the leg towards optical stage 1 is culled per
+    // run from these, iact_cull.cuh leg_masks)
     const int n_chunks = (M + 31) / 32, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int k = warp; k < n_chunks; k += blockDim.x >> 5) {
         const int m = min(32 * k + lane, M - 1);
-        const float4 a = out[2 * m];
+        const float4 a = out[2 * m], nrow = out[2 * m + 1];
         float lo[3] = {a.x, a.y, a.z}, hi[3] = {a.x, a.y, a.z};
         for (int o = 16; o > 0; o >>= 1)
             for (int j = 0; j < 3; ++j) {
@@ -236,9 +238,20 @@ __global__ void __launch_bounds__(256) transform_binned_kernel(const IactFacets 
         const V3 dd = v3(a.x, a.y, a.z) - c;
         float r2 = dot(dd, dd);
         for (int o = 16; o > 0; o >>= 1) r2 = fmaxf(r2, __shfl_xor_sync(0xffffffffu, r2, o));
+        V3 ns = v3(nrow.x, nrow.y, nrow.z);
+        for (int o = 16; o > 0; o >>= 1) {
+            ns.x += __shfl_xor_sync(0xffffffffu, ns.x, o); ns.y += __shfl_xor_sync(0xffffffffu, ns.y, o);
+            ns.z += __shfl_xor_sync(0xffffffffu, ns.z, o);
+        }
+        const float nn = dot(ns, ns);
+        const V3 nbar = nn > 1e-20f ? (1.0f / sqrtf(nn)) * ns : v3(0.f, 0.f, 0.f);
+        const V3 dn = v3(nrow.x, nrow.y, nrow.z) - nbar;
+        float e2 = dot(dn, dn);
+        for (int o = 16; o > 0; o >>= 1) e2 = fmaxf(e2, __shfl_xor_sync(0xffffffffu, e2, o));
         if (lane == 0) {
-            float* cb = chunk_bounds + 4 * ((size_t)(facet_offset + f) * n_chunks + k);
+            float* cb = chunk_bounds + IACT_RUN_BOUND_FLOATS * ((size_t)(facet_offset + f) * n_chunks + k);
             cb[0] = c.x; cb[1] = c.y; cb[2] = c.z; cb[3] = sqrtf(r2) * 1.00001f + 1e-6f;
+            cb[4] = nbar.x; cb[5] = nbar.y; cb[6] = nbar.z; cb[7] = sqrtf(e2) * 1.00001f + 1e-7f;
         }
     }
 }

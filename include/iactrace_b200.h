@@ -37,6 +37,7 @@ extern "C" {
 #define IACT_MAX_STAGES  4   /* optical stages >= 1 (secondary, tertiary, ...) */
 #define IACT_MAX_POLY   16   /* polygon aperture vertices                      */
 #define IACT_MIRROR_REC 24   /* floats per stage>=1 mirror record (below)      */
+#define IACT_RUN_BOUND_FLOATS 8 /* floats per 32-row run in IactScene.chunk_bounds */
 #define IACT_MAX_TAPS   64   /* soft-sensor neighbourhood size                 */
 
 /* JAX key-derivation mode: jax_threefry_partitionable. */
@@ -102,8 +103,9 @@ typedef struct IactScene {
     int32_t      n_facets, n_samples;
     const float* world;    /* device (F, M, 8): px,py,pz,1/weight, nx,ny,nz,(original sample index as int bits) */
     const float* bounds;   /* device (F, 4): bounding sphere of the facet's world points */
-    const float* chunk_bounds; /* device (F, ceil(M/32), 4) or NULL: bounding spheres of each run of 32 consecutive
-                                  table rows, as written by iact_transform_to_world_binned (enables per-iteration culling) */
+    const float* chunk_bounds; /* device (F, ceil(M/32), IACT_RUN_BOUND_FLOATS) or NULL: per run of 32 consecutive table
+                                  rows its bounding sphere (cx,cy,cz,R) and normal cone (unit mean normal, largest
+                                  |n - mean|), as written by iact_transform_to_world_binned (enables per-run culling) */
     /* obstruction groups in the reference's fixed order (obstructions.py:258-278) */
     int32_t n_cyl;  const float *cyl_p1, *cyl_p2, *cyl_r;       /* (K,3)(K,3)(K,)   */
     int32_t n_box;  const float *box_p1, *box_p2;               /* (K,3)(K,3)       */
@@ -192,8 +194,8 @@ int iact_transform_to_world(const IactFacets* facets, int facet_offset,
 
 /* Same transform, but the rows of each facet are written in spatially binned order (counting sort of
  * the samples into a grid_side x grid_side grid of cells over the facet, serpentine cell order), so that
- * every run of 32 consecutive rows covers a small patch; chunk_bounds (Ftot, ceil(M/32), 4) receives the
- * bounding sphere of each run.  Row slot [7] holds the original sample index (int bits), which
+ * every run of 32 consecutive rows covers a small patch; chunk_bounds (Ftot, ceil(M/32), IACT_RUN_BOUND_FLOATS)
+ * receives the bounding sphere and the normal cone of each run.  Row slot [7] holds the original sample index (int bits), which
  * iact_render_debug uses to keep the reference's output order.  Summation order aside, rendering from a
  * binned table is identical to rendering from the plain one. */
 int iact_transform_to_world_binned(const IactFacets* facets, int facet_offset, int grid_side,

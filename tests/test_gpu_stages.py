@@ -165,7 +165,7 @@ def test_sensor_accumulate_entry_point():
 
 
 def test_stage_leg_culling_and_newton_exit_are_exact():
-    """The leg towards the secondary is culled per 32-ray run (occluded_leg_culled) on a spatially binned
+    """The leg towards the secondary is culled per 32-ray run (leg_masks / occluded_leg_culled) on a spatially binned
     sample table, and the Newton scan leaves early once t repeats: both must reproduce the brute-force,
     unbinned run bit for bit, per ray, with obstruction clouds of every type around the light path."""
     from iactrace_b200 import config as Rm
@@ -186,7 +186,11 @@ def test_stage_leg_culling_and_newton_exit_are_exact():
         prims.append(OrientedBox(rng.uniform([-3, -3, 0.5], [3, 3, 6.5]), rng.uniform(0.02, 0.2, 3), q.astype(np.float32)))
         v0 = rng.uniform([-3, -3, 0.5], [3, 3, 6.5])
         prims.append(Triangle(v0, v0 + rng.normal(size=3) * 0.3, v0 + rng.normal(size=3) * 0.3))
-    for plist in (prims[:6], prims):
+    # <= 32 primitives: the leg is culled per run from the bounding spheres and normal cones (leg_masks), for shared
+    # directions and for point sources near enough to have parallax over a run; more: per iteration from the rays
+    near = (-300.0 * src).astype(np.float32)
+    for plist, srcs, stype in ((prims[:6], src, "parallel"), (prims[:30], src, "parallel"), (prims[:30], near, "point"),
+                               (prims, src, "parallel")):
         tel = I.Telescope(base.mirror_groups, group_obstructions(plist), base.sensors)
         out = []
         for cull, bin_min in ((True, 256), (False, 0)):
@@ -194,8 +198,8 @@ def test_stage_leg_culling_and_newton_exit_are_exact():
             Rm.bin_samples_min = bin_min
             try:
                 tel._cache.pop("world", None)
-                xy, v = render_debug(tel, src, val, "parallel", 0)
-                img = render(tel, src, val, "parallel", 0)
+                xy, v = render_debug(tel, srcs, val, stype, 0)
+                img = render(tel, srcs, val, stype, 0)
                 out.append((xy.cpu().numpy(), v.cpu().numpy(), img.cpu().numpy()))
             finally:
                 Rm.cull_obstructions, Rm.bin_samples_min = True, old_bin

@@ -172,12 +172,17 @@ def test_binned_table_and_sub_beam_culling_are_exact():
     keep = []
     sc, _ = build_scene(tel, 0, keep)
     world, bounds, chunks = keep[0], keep[1], keep[2]
-    assert chunks is not None and chunks.shape == (world.shape[0], (300 + 31) // 32, 4)
+    assert chunks is not None and chunks.shape == (world.shape[0], (300 + 31) // 32, 8)
     p = world[..., 0:3]
     for k in range(chunks.shape[1]):
         rows = p[:, 32 * k:32 * k + 32]
         d = (rows - chunks[:, k:k + 1, 0:3]).norm(dim=-1).max(dim=1).values
         assert bool((d <= chunks[:, k, 3] + 1e-6).all())
+        # ... and the normal cones their normals (unit mean normal, largest distance from it)
+        nrm = world[:, 32 * k:32 * k + 32, 4:7]
+        e = (nrm - chunks[:, k:k + 1, 4:7]).norm(dim=-1).max(dim=1).values
+        assert bool((e <= chunks[:, k, 7] + 1e-7).all())
+        assert bool(((chunks[:, k, 4:7].norm(dim=-1) - 1).abs() < 1e-5).all())
     # binning is a permutation of the samples
     idx = world[..., 7].contiguous().view(torch.int32).sort(dim=1).values
     assert bool((idx == torch.arange(300, device=idx.device, dtype=torch.int32)[None]).all())

@@ -6,6 +6,7 @@ With a bench workload name the first kernel's figures also go to profiles/ncu_fi
 roofline.traffic / executed_fp32_frac / issue_slot_util / atomic.
 """
 import json
+import os
 from pathlib import Path
 import csv
 import subprocess
@@ -93,7 +94,7 @@ def main():
     if agg:
         ti, ts = sum(a[0] for a in agg) or 1, sum(a[1] for a in agg) or 1
         lines.append("## hottest source lines (share of warp instructions / of stall samples)")
-        for a in sorted(agg, key=lambda a: -a[0])[:30]:
+        for a in sorted(agg, key=lambda a: -a[0])[:int(os.environ.get("NCU_TOP_LINES", "30"))]:
             lines.append(f"{100 * a[0] / ti:5.1f}% inst {100 * a[1] / ts:5.1f}% smp  {a[2]}:{a[3]}  {a[4]}")
     open(out, "w").write("\n".join(lines) + "\n")
     if figures:
