@@ -322,7 +322,7 @@ struct PixCache {
 #endif                               // spills) beat four at 62 by 2-4 % (r2: also with level-3 culling, M = 4096: 87.3 -> 83.5 ms);
                                      // square cameras and the response matrix lose 2-20 % at five (spills) and stay at four
 #ifndef IACT_MIN_BLOCKS_STAGES
-#define IACT_MIN_BLOCKS_STAGES 3
+#define IACT_MIN_BLOCKS_STAGES 4
 #endif
 #ifndef IACT_MIN_BLOCKS_SOFT
 #define IACT_MIN_BLOCKS_SOFT 4       // soft hex cameras: two 7-tap register caches per warp
