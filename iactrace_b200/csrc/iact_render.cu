@@ -389,7 +389,7 @@ __device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx
         d = scale_rn(frsqrt_nr_rn(dot_rn(d, d)), d);
     }
     // render.py:138 shadow of the incoming leg (infinite ray back towards the source)
-    const bool blocked = occluded<SUB, true>(ob, o, -d, cx.list, n_list_cyl, n_list, sub_mask, cx.wrec, n_rec);
+    const bool blocked = occluded<SUB>(ob, o, -d, cx.list, n_list_cyl, n_list, sub_mask, cx.wrec, n_rec);
     // render.py:140-141, reflection.py:17-19
     const float c = dot_rn(d, n);
     d = fma_rn(__fmul_rn(-2.0f, c), n, d);
