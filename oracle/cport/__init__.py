@@ -10,7 +10,7 @@ import ctypes as C
 
 import numpy as np
 
-from .build import build, build_native, LIB
+from .build import build, build_f64, build_native, LIB
 from .. import trace as otrace
 
 
@@ -25,10 +25,16 @@ class _Sensor(C.Structure):
 
 _lib = None
 _lib_native = None
+_lib_f64 = None
 
 
 def _load(variant="exact"):
-    global _lib, _lib_native
+    global _lib, _lib_native, _lib_f64
+    if variant == "f64":
+        if _lib_f64 is None:
+            _lib_f64 = C.CDLL(str(build_f64()))
+            _lib_f64.oracle_render.restype = C.c_int
+        return _lib_f64
     if variant == "native":
         if _lib_native is None:
             _lib_native = C.CDLL(str(build_native()))
@@ -97,7 +103,8 @@ def prepare(scene, sensor_idx=0):
 
 def render(prep, sources, values, source_type="point", debug=False, threads=0, variant="exact"):
     """-> (image, n_threads_used) or, with debug, (xy, vals) in render_debug order.  ``variant="native"`` uses the
-    -O3 -march=native build (timing only; the parity tests use the bit-exact one)."""
+    -O3 -march=native build (timing only; the parity tests use the bit-exact one), ``variant="f64"`` the build whose
+    per-ray chain runs in float64 (inputs and outputs stay float32 arrays)."""
     lib = _load(variant)
     src = np.ascontiguousarray(sources, np.float32)
     val = np.ascontiguousarray(values, np.float32)

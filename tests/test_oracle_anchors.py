@@ -71,6 +71,14 @@ def test_c_port_is_bit_identical_to_numpy_oracle(stype, sensor_idx):
     img, _ = cport.render(prep, src, val, stype, threads=3)
     oimg = otrace.render(sc, src, val, stype, sensor_idx, np.float32)
     np.testing.assert_allclose(img, oimg, rtol=1e-5, atol=1e-6 * oimg.max())
+    # the float64 build of the same source (tools/parity_fullsize.py) against the NumPy oracle in float64
+    xy64, v64 = cport.render(prep, src, val, stype, debug=True, variant="f64")
+    oxy64, ov64 = otrace.render_debug(sc, src, val, stype, sensor_idx, np.float64)
+    assert np.array_equal(v64 == 0, ov64 == 0)
+    np.testing.assert_allclose(v64, ov64, rtol=2e-7, atol=1e-12)
+    hit = np.abs(oxy64) < 1e9
+    # (the C port takes float32 world tables, the NumPy oracle transforms in float64: 6e-8 on a normal x 36 m)
+    np.testing.assert_allclose(xy64[hit], oxy64[hit], rtol=2e-7, atol=1e-5)
 
 
 def test_response_matrix_and_render_consistency():
