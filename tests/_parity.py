@@ -21,7 +21,7 @@ import numpy as np
 EDGE_MARGIN = 1e-5   # metres: rays closer than this to a pixel edge may land on either side
 
 
-def compare_rays(tel, src, val, stype, sensor_idx, xy_tol=2e-5, flip_budget=2e-4, edge_budget=5e-2):
+def compare_rays(tel, src, val, stype, sensor_idx, xy_tol=2e-5, flip_budget=2e-5, edge_budget=5e-2):
     """Per-ray parity of ``render_debug`` against the float64 oracle.  Returns the arrays the image checks need
     plus a ``stats`` dict with the measured rates."""
     from iactrace_b200.core import render_debug
@@ -42,7 +42,7 @@ def subset_rays(r, mask):
     return {k: (a[mask] if isinstance(a, np.ndarray) and a.shape[:1] == mask.shape else a) for k, a in r.items()}
 
 
-def ray_parity(xy, v, pix, oxy, ov, s, xy_tol=2e-5, flip_budget=2e-4, edge_budget=5e-2, value_rtol=1e-5, index_dt=np.float64):
+def ray_parity(xy, v, pix, oxy, ov, s, xy_tol=2e-5, flip_budget=2e-5, edge_budget=5e-2, value_rtol=1e-5, index_dt=np.float64):
     """Per-ray comparison of the kernel's (xy, v, pix) with reference rays (oxy, ov) on oracle sensor ``s``; the
     reference pixel index is the oracle's binning of (oxy) in ``index_dt`` arithmetic."""
     from oracle import trace as otrace

@@ -47,10 +47,11 @@ def test_ct3_config1_on_axis_point_source(sensor_idx):
     r = _compare_rays(tel, src, val, "point", sensor_idx)
     img = render(tel, src, val, "point", sensor_idx).cpu().numpy()
     assert img.shape == tuple(tel.sensors[sensor_idx].get_accumulator_shape())
-    # Hex camera: the 3.8e5 rays of the on-axis spot fall into FOUR 4 cm pixels of ~9e4 rays each; the ~40 rays that
-    # flip their shadow decision (rate 1.1e-4, below the float32 oracle's own 1.5e-4: profiles/parity_r02*.json) touch
-    # all four, so no pixel is "clean" -- but they weigh 1e-5 of a pixel: every bright pixel is compared at the 1e-4
-    # bar WITH them.  Lid: ~300 1 mm pixels of ~1e3 rays each, about half of them free of rays that moved by a pixel.
+    # Hex camera: the 3.8e5 rays of the on-axis spot fall into FOUR 4 cm pixels of ~9e4 rays each.  No ray flips its
+    # shadow decision against the float64 oracle any more (cancellation-free discriminant, iact_trace.cuh cyl_hit;
+    # profiles/parity_r02.json), but the handful of rays within micrometres of a pixel edge touch all four pixels, so
+    # no pixel is "clean": every bright pixel is compared at the 1e-4 bar WITH them (they weigh 1e-5 of a pixel).
+    # Lid: ~300 1 mm pixels of ~1e3 rays each, about half of them free of rays that moved by a pixel.
     if sensor_idx == 0:
         st = _compare_image(img, r, img.shape, min_lit=0, min_flux_share=0.0, dense_rtol=1e-4)
     else:
