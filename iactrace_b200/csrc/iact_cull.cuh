@@ -156,7 +156,7 @@ __device__ __forceinline__ int build_list_uni(const ObsSmem& ob, const Beam& b, 
             c = ob.cyl + CYL_STRIDE * id;
             const V3 p1 = v3(c[0], c[1], c[2]), ax = v3(c[3], c[4], c[5]);
             const float h = c[6], r = fabsf(c[7]) * 1.0001f;
-            cd = cyl_dir(ax, b.u);
+            cd = cyl_dir(ax, __fmul_rn(c[7], c[7]), b.u);
             const V3 a1 = p1 - b.c;
             const float t1 = dot(a1, b.u), t2 = t1 + h * cd.rd_ax;
             const float tmx = fmaxf(t1, t2);
@@ -181,11 +181,7 @@ __device__ __forceinline__ int build_list_uni(const ObsSmem& ob, const Beam& b, 
     if (keep) {
         out[pos] = (unsigned short)id;
         if (c && pos < CYL_REC_MAX) {
-            float4* q = reinterpret_cast<float4*>(wrec + CYL_REC * pos);
-            q[0] = make_float4(c[0], c[1], c[2], c[6]);
-            q[1] = make_float4(c[3], c[4], c[5], __fmul_rn(c[7], c[7]));
-            q[2] = make_float4(cd.rdp2.x, cd.rdp2.y, cd.rdp2.z, cd.rd_ax);
-            q[3] = make_float4(cd.a4, cd.inv2a, cd.inv_ax, cd.a);
+            cyl_record_store(wrec + CYL_REC * pos, c, cd);
         }
     }
     n_cyl_out = n_cand_cyl >= 32 ? __popc(mask) : __popc(mask & ((1u << n_cand_cyl) - 1u));

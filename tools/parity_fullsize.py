@@ -39,12 +39,19 @@ def main():
     osc = to_oracle_scene(tel)
     src = point_grid(side, 1.5)
     val = np.ones(len(src), np.float32)
+    n_rays = len(src) * sum(len(g) for g in tel.mirror_groups) * 115
+
     def diff(a, b):
         """Per-pixel relative difference of image a from image b, on b's lit pixels."""
         lit = b > 0
         rel = np.abs(a - b)[lit] / b[lit]
         bright = b[lit] >= 1e-3 * b.max()
+        ray = b.sum() / n_rays                                   # mean value of one ray
+        over = rel > 1e-4
+        worst = dict(pixels_above_1e4th_rays_equivalent_min_max=[float((b[lit][over] / ray).min()), float((b[lit][over] / ray).max())],
+                     pixels_above_1e4th_net_rays_moved_max=float((np.abs(a - b)[lit][over] / ray).max())) if over.any() else {}
         return dict(lit_pixels=int(lit.sum()), bright_pixels_ge_1permille_of_max=int(bright.sum()),
+                    max_net_rays_moved_per_pixel=float((np.abs(a - b)[lit] / ray).max()), **worst,
                     max_rel_diff_lit_pixels=float(rel.max()), median_rel_diff_lit_pixels=float(np.median(rel)),
                     max_rel_diff_bright_pixels=float(rel[bright].max()), lit_pixels_above_1e4th=int((rel > 1e-4).sum()),
                     total_flux_rel_diff=float((a.sum() - b.sum()) / b.sum()),
@@ -59,7 +66,6 @@ def main():
             o, nt = cport.render(prep, src, val, "point", variant=variant)
             secs[variant] = round(time.time() - t0, 1)
             imgs[variant] = o.astype(np.float64)
-        n_rays = len(src) * sum(len(g) for g in tel.mirror_groups) * 115
         out["cases"][name] = dict(
             rays=n_rays, pixels=int(img.size), oracle_threads=int(nt), oracle_seconds=secs,
             min_rays_equivalent_of_a_lit_pixel=float(imgs["f64"][imgs["f64"] > 0].min() / (imgs["f64"].sum() / n_rays)),
