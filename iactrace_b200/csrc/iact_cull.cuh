@@ -141,10 +141,10 @@ __device__ __forceinline__ int build_list(const ObsSmem& ob, const Beam& b, cons
 // with p2 = p1 + h ax the segment in the plane normal to u is q1 + s h (ax - (ax.u) u), of squared length h^2 a.  Same
 // margins as beam_keeps_capsule (the axis of the staged table differs from (p2 - p1) / h by float32 rounding, ~1e-7 h,
 // against 2 mm).  Kept cylinders write their record at their compacted position; other primitives go through the
-// proxy test.  Returns the list length, sets n_cyl_out; records beyond CYL_REC_MAX are not written (the ray loop
-// finishes those inline).
+// proxy test.  Returns the list length, sets n_cyl_out and n_rec_out = how many leading list entries the ray loop may
+// test through their records (at most CYL_REC_MAX, and none from the first literal-form cylinder on; the rest inline).
 __device__ __forceinline__ int build_list_uni(const ObsSmem& ob, const Beam& b, const unsigned short* __restrict__ cand, int n_cand_cyl,
-                                              int n_cand, unsigned short* out, float* wrec, int& n_cyl_out) {
+                                              int n_cand, unsigned short* out, float* wrec, int& n_cyl_out, int& n_rec_out) {
     const unsigned lane = threadIdx.x & 31u;
     bool keep = false;
     int id = 0;
@@ -185,6 +185,10 @@ __device__ __forceinline__ int build_list_uni(const ObsSmem& ob, const Beam& b, 
         }
     }
     n_cyl_out = n_cand_cyl >= 32 ? __popc(mask) : __popc(mask & ((1u << n_cand_cyl) - 1u));
+    // records hold the interval form only: they end before the first kept cylinder the direction is nearly parallel to
+    const unsigned lit = __ballot_sync(0xffffffffu, keep && c && !cyl_interval_form(cd));
+    const int first_lit = lit ? __popc(mask & ((1u << (__ffs(lit) - 1)) - 1u)) : CYL_REC_MAX;
+    n_rec_out = min(min(n_cyl_out, CYL_REC_MAX), first_lit);
     __syncwarp();
     return __popc(mask);
 }

@@ -509,15 +509,16 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
             beam.c = v3(bnd.x, bnd.y, bnd.z); beam.R = bnd.w; beam.spread = 0.f; beam.u = -sd; beam.ok = true;
             beam.invD = 0.f;
             if (SRC == IACT_SOURCE_POINT) { const V3 ac = sub_rn(beam.c, src); beam.invD = frsqrt_fast(dot_rn(ac, ac)); }
-            n_list = build_list_uni(cx.ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, cx.list, cx.wrec, n_list_cyl);
-            n_rec = min(n_list_cyl, CYL_REC_MAX);
+            n_list = build_list_uni(cx.ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, cx.list, cx.wrec, n_list_cyl, n_rec);
         } else {
             beam = make_beam<SRC>(bnd, src);
             n_list = item_list(cx, fl, beam, f, n_list_cyl);
             if (want_rec) {
                 n_rec = min(n_list_cyl, CYL_REC_MAX);
-                if (lane < n_rec) cyl_record_write(cx.wrec + CYL_REC * lane, cx.ob.cyl + CYL_STRIDE * cx.list[lane], -sd);
-                __syncwarp();
+                bool literal = false;
+                if (lane < n_rec) literal = !cyl_record_write(cx.wrec + CYL_REC * lane, cx.ob.cyl + CYL_STRIDE * cx.list[lane], -sd);
+                const unsigned lm = __ballot_sync(0xffffffffu, literal);      // (also orders the record writes before the reads)
+                if (lm) n_rec = __ffs(lm) - 1;
             }
         }
     }

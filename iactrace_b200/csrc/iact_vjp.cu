@@ -430,8 +430,7 @@ vjp_kernel(const __grid_constant__ SceneDev sc, const IactFacets fa, const float
                     beam.c = v3(bnd.x, bnd.y, bnd.z); beam.R = bnd.w; beam.spread = 0.f; beam.u = -sd; beam.ok = true;
                     beam.invD = 0.f;
                     if (SRC == IACT_SOURCE_POINT) { const V3 ac = sub_rn(beam.c, src); beam.invD = frsqrt_fast(dot_rn(ac, ac)); }
-                    n_list = build_list_uni(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, wrec, n_list_cyl);
-                    n_rec = min(n_list_cyl, CYL_REC_MAX);
+                    n_list = build_list_uni(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, wrec, n_list_cyl, n_rec);
                 } else {
                     const Beam beam = make_beam<SRC>(bnd, src);
                     if (cnt.x >= 0) n_list = build_list(ob, beam, fl.ids + (size_t)f * fl.stride, cnt.x, cnt.y, list, n_list_cyl);
