@@ -9,7 +9,7 @@ timeout 900 python bench.py > gpurun_out/bench_default.jsonl 2> gpurun_out/bench
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.jsonl 2>/dev/null; tail -c 900 gpurun_out/bench_reference.jsonl
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/b_ncu.log 2>&1
 timeout 600 python tools/check_fmad_invariance.py > gpurun_out/fmad_invariance.log 2>&1; tail -2 gpurun_out/fmad_invariance.log
-bash tools/gpu_profile_text.sh trace_v12 trace_kernel 3 4.126e8 ct5_point_4096x115_hex
+bash tools/gpu_profile_text.sh trace_v13 trace_kernel 3 4.126e8 ct5_point_4096x115_hex
 
 
 ls -la gpurun_out | tail -8
