@@ -307,6 +307,9 @@ struct PixCache {
 #ifndef IACT_UNI_LIST
 #define IACT_UNI_LIST 1      // level-2 list and cylinder records of a shared-direction item in one pass
 #endif
+#ifndef IACT_STAGE_SIMPLE
+#define IACT_STAGE_SIMPLE 1  // lean path for stages that are one conic mirror with a circular aperture (reflect_at_stage_simple)
+#endif
 #ifndef IACT_LEG_MASKS
 #define IACT_LEG_MASKS 1     // leg towards optical stage 1 culled per 32-row run of a binned table (not per iteration)
 #endif
@@ -336,6 +339,7 @@ struct TraceCtx {
     unsigned short* list;
     float* wrec;              // this warp's CylRec records (CYL_REC_MAX x CYL_REC floats) or nullptr
     bool cull, soft;
+    bool stage_simple;        // every optical stage >= 1 is one conic mirror with a circular aperture (reflect_at_stage_simple)
 };
 
 // Per-block set-up shared by the trace kernels: obstruction tables, stage records, histogram, lookup table
@@ -368,6 +372,13 @@ __device__ __forceinline__ void trace_setup(const SceneDev& sc, float* smem, Tra
     cx.list = cx.cull ? reinterpret_cast<unsigned short*>(p) + (size_t)warp * ((n_obs + 1) & ~1) : nullptr;
     cx.soft = SENS == SENS_SQUARE ? sc.sens.kind == IACT_SENSOR_SOFT_SQUARE : SENS == SENS_SOFT_HEX;
     __syncthreads();
+    cx.stage_simple = false;
+    if (STAGES && IACT_STAGE_SIMPLE) {
+        bool simple = sc.n_stages > 0;
+        const float* r = cx.stage_rec;
+        for (int st = 0; st < sc.n_stages; ++st) { simple = simple && stage_is_simple(sc.stages[st].n, r); r += (size_t)sc.stages[st].n * STAGE_REC; }
+        cx.stage_simple = simple;
+    }
 }
 
 // One ray from table row (a, b) of a facet: shadow of the incoming leg, reflection, optical stages >= 1, sensor
@@ -406,7 +417,8 @@ __device__ __forceinline__ void trace_ray(const SceneDev& sc, const TraceCtx& cx
                     if (need) leg_blocked |= hit_primitive(ob, p, o, d);
                 }
             } else leg_blocked = occluded_leg_culled(ob, o, d, val != 0.f);
-            reflect_at_stage(sc.stages[st].n, rec, sc.stages[st].verts, leg_blocked, !cx.cull, o, d, val);
+            if (cx.stage_simple) reflect_at_stage_simple(rec, leg_blocked, !cx.cull, o, d, val);
+            else reflect_at_stage(sc.stages[st].n, rec, sc.stages[st].verts, leg_blocked, !cx.cull, o, d, val);
             rec += (size_t)sc.stages[st].n * STAGE_REC;
         }
     }
