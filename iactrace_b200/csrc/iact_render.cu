@@ -307,6 +307,9 @@ struct PixCache {
 #ifndef IACT_UNI_LIST
 #define IACT_UNI_LIST 1      // level-2 list and cylinder records of a shared-direction item in one pass
 #endif
+#ifndef IACT_REC_MIN_ROWS
+#define IACT_REC_MIN_ROWS 33 // rows per warp item from which cylinder records (and the one-pass level-2 list) are used
+#endif
 #ifndef IACT_STAGE_SIMPLE
 #define IACT_STAGE_SIMPLE 1  // lean path for stages that are one conic mirror with a circular aperture (reflect_at_stage_simple)
 #endif
@@ -509,9 +512,10 @@ __device__ __forceinline__ void trace_item(const SceneDev& sc, const TraceCtx& c
         const float n2 = dot_rn(ac, ac);
         if (bnd.w * bnd.w < 1e-18f * n2 && n2 < 1e37f) { uni = true; sd = scale_rn(frsqrt_nr_rn(n2), ac); }
     }
-    // records pay from three 32-ray iterations per item on (CT3 response matrix at M = 64: 1.125 -> 1.10 ms without) and
-    // not in the stage >= 1 kernels, which are short of registers (Cassegrain: 32.4 -> 31.1 ms without)
-    const bool want_rec = IACT_CYL_RECORDS && !STAGES && uni && cx.wrec && m1 - m0 > 64;
+    // records pay from two 32-ray iterations per item on (CT3 response matrix at M = 64: 1.148 -> 1.067 ms; since the list
+    // and the records come out of one pass they cost an item nothing extra) and are not used in the stage >= 1 kernels,
+    // which are short of registers
+    const bool want_rec = IACT_CYL_RECORDS && !STAGES && uni && cx.wrec && m1 - m0 >= IACT_REC_MIN_ROWS;
     if (cx.cull) {
         const int2 cnt = fl.count ? __ldg(fl.count + f) : make_int2(-1, -1);
         // (parallel directions are not normalised by the library: the one-pass form needs a unit direction)
